@@ -1,0 +1,317 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.
+
+ctypes loader for oracle/_build/libpgo_oracle.so (the CPU restatement of the reference hot path).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module; the product package never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "_build", "libpgo_oracle.so")
+
+_dp = C.POINTER(C.c_double)
+_u64p = C.POINTER(C.c_uint64)
+_i64p = C.POINTER(C.c_int64)
+_u32p = C.POINTER(C.c_uint32)
+_u16p = C.POINTER(C.c_uint16)
+_u8p = C.POINTER(C.c_uint8)
+_ip = C.POINTER(C.c_int)
+_fp = C.POINTER(C.c_float)
+
+
+def build(force=False):
+    """Compile the oracle with its Makefile (g++, reference flags, no FMA contraction)."""
+    if force or not os.path.exists(_LIB) or any(
+        os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB)
+        for f in os.listdir(_HERE)
+        if f.endswith((".hpp", ".cpp")) or f == "Makefile"
+    ):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB):
+            build()
+        _lib = C.CDLL(_LIB)
+        _lib.pgo_get_inliers.restype = C.c_uint64
+        _lib.pgo_pairlog_size.restype = C.c_uint64
+        _lib.pgo_run_scene.restype = C.c_void_p
+        _lib.pgo_run_log_count.restype = C.c_uint64
+    return _lib
+
+
+def _d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+PAIRLOG_DTYPE = np.dtype(
+    [
+        ("src", np.uint32), ("dst", np.uint32), ("pairIndex", np.int64),
+        ("visible", np.uint8), ("hadPath", np.uint8), ("testPassed", np.uint8), ("branch", np.uint8),
+        ("committed", np.uint8),
+        ("testCount", np.uint32), ("inlierNumber", np.uint32), ("nCorr", np.uint32), ("touchedNodes", np.uint32),
+        ("E", np.float64, (9,)), ("q", np.float64, (4,)), ("t", np.float64, (3,)), ("score", np.float64),
+    ],
+    align=True,
+)
+
+
+# ---- geometry ---------------------------------------------------------------------------------------
+def sampson_sq(corr, E):
+    corr, E = _d(corr), _d(E).reshape(9)
+    out = np.empty(len(corr))
+    lib().pgo_sampson_sq(_p(corr, _dp), C.c_uint64(len(corr)), _p(E, _dp), _p(out, _dp))
+    return out
+
+
+def essential_from_pose(qt):
+    qt = _d(qt)
+    E = np.empty(9)
+    lib().pgo_essential_from_pose(_p(qt, _dp), _p(E, _dp))
+    return E.reshape(3, 3)
+
+
+def se3_mul(a, b):
+    a, b = _d(a), _d(b)
+    out = np.empty(7)
+    lib().pgo_se3_mul(_p(a, _dp), _p(b, _dp), _p(out, _dp))
+    return out
+
+
+def se3_inverse(a):
+    a = _d(a)
+    out = np.empty(7)
+    lib().pgo_se3_inverse(_p(a, _dp), _p(out, _dp))
+    return out
+
+
+def rotation_to_quat(R):
+    R = _d(R).reshape(9)
+    q = np.empty(4)
+    lib().pgo_rotation_to_quat(_p(R, _dp), _p(q, _dp))
+    return q
+
+
+def quat_to_rotation(q):
+    q = _d(q)
+    R = np.empty(9)
+    lib().pgo_quat_to_rotation(_p(q, _dp), _p(R, _dp))
+    return R.reshape(3, 3)
+
+
+def test_pose(corr, qt, thr, min_inliers=5):
+    corr, qt = _d(corr), _d(qt)
+    cnt = C.c_uint64(0)
+    ok = lib().pgo_test_pose(_p(corr, _dp), C.c_uint64(len(corr)), _p(qt, _dp), C.c_double(thr),
+                             C.c_uint64(min_inliers), C.byref(cnt))
+    return bool(ok), int(cnt.value)
+
+
+def get_inliers(corr, E, thr):
+    corr, E = _d(corr), _d(E).reshape(9)
+    idx = np.empty(len(corr), dtype=np.uint64)
+    n = lib().pgo_get_inliers(_p(corr, _dp), C.c_uint64(len(corr)), _p(E, _dp), C.c_double(thr), _p(idx, _u64p))
+    return idx[:n].copy()
+
+
+def create_correspondences(kp_src, kp_dst, matches, fx, fy, cx, cy, thr_px):
+    kp_src = np.ascontiguousarray(kp_src, dtype=np.float32)
+    kp_dst = np.ascontiguousarray(kp_dst, dtype=np.float32)
+    matches = np.ascontiguousarray(matches, dtype=np.uint32)
+    n = len(matches)
+    corr = np.empty((n, 4))
+    thr = C.c_double(0)
+    lib().pgo_create_correspondences(_p(kp_src, _fp), _p(kp_dst, _fp), _p(matches, _u32p), C.c_uint64(n),
+                                     C.c_double(fx), C.c_double(fy), C.c_double(cx), C.c_double(cy),
+                                     C.c_double(thr_px), _p(corr, _dp), C.byref(thr))
+    return corr, thr.value
+
+
+# ---- OpenCV-owned stages ------------------------------------------------------------------------------
+def cv_rng(seed, n):
+    out = np.empty(n, dtype=np.uint32)
+    lib().pgo_cv_rng(C.c_uint64(seed), C.c_uint64(n), _p(out, _u32p))
+    return out
+
+
+def cv_svd_5x9(Q):
+    Q = _d(Q).reshape(45)
+    Vt, W = np.empty(81), np.empty(5)
+    lib().pgo_cv_svd_5x9(_p(Q, _dp), _p(Vt, _dp), _p(W, _dp))
+    return W, Vt.reshape(9, 9)
+
+
+def cv_solvez3(B):
+    B = _d(B).reshape(9)
+    out = np.empty(3)
+    lib().pgo_cv_solvez3(_p(B, _dp), _p(out, _dp))
+    return out
+
+
+def cv_invert10(A):
+    A = _d(A).reshape(100)
+    inv = np.empty(100)
+    ok = lib().pgo_cv_invert10(_p(A, _dp), _p(inv, _dp))
+    return bool(ok), inv.reshape(10, 10)
+
+
+def cv_solve_poly(c, max_iters=1000, tol_sq=0.0):
+    c = _d(c)
+    n0 = len(c) - 1
+    r = np.empty(2 * n0)
+    n = lib().pgo_cv_solve_poly(_p(c, _dp), C.c_int(n0), _p(r, _dp), C.c_int(max_iters), C.c_double(tol_sq))
+    return r[: 2 * n].reshape(n, 2)
+
+
+def five_point(x1, x2, dk_max_iters=1000, dk_tol_sq=0.0):
+    x1, x2 = _d(x1).reshape(10), _d(x2).reshape(10)
+    E = np.empty(90)
+    n = lib().pgo_five_point(_p(x1, _dp), _p(x2, _dp), _p(E, _dp), C.c_int(dk_max_iters), C.c_double(dk_tol_sq))
+    return E[: 9 * n].reshape(n, 3, 3)
+
+
+def find_essential_ransac_inf(pts):
+    pts = _d(pts)
+    n = len(pts)
+    E = np.empty(90)
+    mask = np.zeros(max(n, 1), dtype=np.uint8)
+    sample = np.zeros(5, dtype=np.int32)
+    iters = C.c_int(0)
+    nm = lib().pgo_find_essential_ransac_inf(_p(pts, _dp), C.c_int(n), _p(E, _dp), _p(mask, _u8p), _p(sample, _ip),
+                                             C.byref(iters))
+    return nm, E[: 9 * max(nm, 0)].reshape(-1, 3, 3), mask[:n], sample, iters.value
+
+
+# ---- Eigen-owned stages -------------------------------------------------------------------------------
+def eigen_svd(A):
+    A = _d(A)
+    n = A.shape[0]
+    U, V, S = np.empty(n * n), np.empty(n * n), np.empty(n)
+    f = lib().pgo_eigen_svd3 if n == 3 else lib().pgo_eigen_svd4
+    f(_p(A.reshape(-1), _dp), _p(U, _dp), _p(V, _dp), _p(S, _dp))
+    return U.reshape(n, n), S, V.reshape(n, n)
+
+
+def decompose_essential(E):
+    E = _d(E).reshape(9)
+    R1, R2, t = np.empty(9), np.empty(9), np.empty(3)
+    lib().pgo_decompose_essential(_p(E, _dp), _p(R1, _dp), _p(R2, _dp), _p(t, _dp))
+    return R1.reshape(3, 3), R2.reshape(3, 3), t
+
+
+def pose_from_essential(E, corr):
+    E, corr = _d(E).reshape(9), _d(corr)
+    R, t = np.empty(9), np.empty(3)
+    votes = np.zeros(4, dtype=np.uint64)
+    lib().pgo_pose_from_essential(_p(E, _dp), _p(corr, _dp), C.c_uint64(len(corr)), _p(R, _dp), _p(t, _dp),
+                                  _p(votes, _u64p))
+    return R.reshape(3, 3), t, votes
+
+
+# ---- fallback -------------------------------------------------------------------------------------------
+def sampler_table(N, iters=1000):
+    out = np.empty(iters * 5, dtype=np.uint32)
+    lib().pgo_sampler_table(C.c_int(N), C.c_int(iters), _p(out, _u32p))
+    return out.reshape(iters, 5)
+
+
+def iters_table(N):
+    out = np.empty(N + 1, dtype=np.uint16)
+    lib().pgo_iters_table(C.c_int(N), _p(out, _u16p))
+    return out
+
+
+def score_model(corr, E, thr):
+    corr, E = _d(corr), _d(E).reshape(9)
+    cost, inl = C.c_double(0), C.c_int(0)
+    lib().pgo_score_model(_p(corr, _dp), C.c_int(len(corr)), _p(E, _dp), C.c_double(thr), C.byref(cost), C.byref(inl))
+    return cost.value, inl.value
+
+
+def ls_refit(corr, E, thr):
+    corr, E = _d(corr), _d(E).reshape(9)
+    out = np.empty(9)
+    ok = lib().pgo_ls_refit(_p(corr, _dp), C.c_int(len(corr)), _p(E, _dp), C.c_double(thr), _p(out, _dp))
+    return bool(ok), out.reshape(3, 3)
+
+
+def fallback(corr, thr):
+    corr = _d(corr)
+    E = np.empty(9)
+    mask = np.zeros(len(corr), dtype=np.uint8)
+    info = np.zeros(5, dtype=np.int32)
+    lib().pgo_fallback(_p(corr, _dp), C.c_int(len(corr)), C.c_double(thr), _p(E, _dp), _p(mask, _u8p), _p(info, _ip))
+    return dict(ok=int(info[0]), inliers=int(info[1]), iterations=int(info[2]), models=int(info[3]),
+                lo_runs=int(info[4]), E=E.reshape(3, 3), mask=mask)
+
+
+# ---- estimatePose -----------------------------------------------------------------------------------------
+def estimate_pose(corr, thr_norm, guesses=(), min_inliers=20):
+    corr = _d(corr)
+    g = _d(np.asarray(guesses, dtype=np.float64).reshape(-1, 7)) if len(guesses) else np.zeros((0, 7))
+    E, qt = np.empty(9), np.empty(7)
+    mask = np.zeros(len(corr), dtype=np.uint8)
+    info = np.zeros(8, dtype=np.int64)
+    lib().pgo_estimate_pose(_p(corr, _dp), C.c_uint64(len(corr)), C.c_double(thr_norm), C.c_uint64(min_inliers),
+                            _p(g, _dp), C.c_uint64(len(g)), _p(E, _dp), _p(qt, _dp), _p(mask, _u8p), _p(info, _i64p))
+    return dict(success=bool(info[0]), branch=int(info[1]), inlier_number=int(info[2]), path_inliers=int(info[3]),
+                votes=info[4:8].copy(), E=E.reshape(3, 3), pose=qt, mask=mask)
+
+
+def estimate_pose_batch(corr, offset, thr_norm, guesses, has_guess, min_inliers=20, threads=0):
+    corr = _d(corr)
+    offset = np.ascontiguousarray(offset, dtype=np.uint64)
+    thr_norm = _d(thr_norm)
+    guesses = _d(guesses)
+    has_guess = np.ascontiguousarray(has_guess, dtype=np.uint8)
+    n = len(offset) - 1
+    E, qt = np.empty((n, 9)), np.empty((n, 7))
+    info = np.zeros((n, 8), dtype=np.int64)
+    used = lib().pgo_estimate_pose_batch(_p(corr, _dp), _p(offset, _u64p), C.c_uint64(n), _p(thr_norm, _dp),
+                                         C.c_uint64(min_inliers), _p(guesses, _dp), _p(has_guess, _u8p), _p(E, _dp),
+                                         _p(qt, _dp), _p(info, _i64p), C.c_int(threads))
+    return dict(E=E, pose=qt, info=info, threads=used)
+
+
+# ---- host loop ----------------------------------------------------------------------------------------------
+def run_scene(scene, sim_threshold=0.0, thr_px=0.4, min_inliers=20, min_points=50, max_depth=5, weight=0.8,
+              use_path_finding=True, max_pairs=0):
+    """scene: dict with focal[V], size[V,2], sim[V,V], kp_offset[V+1], kp[K,2] f32, pair_views[P,2] u32,
+    m_offset[P+1] u64, matches[M,2] u32 (the container of SURVEY App. D)."""
+    L = lib()
+    assert L.pgo_pairlog_size() == PAIRLOG_DTYPE.itemsize, (L.pgo_pairlog_size(), PAIRLOG_DTYPE.itemsize)
+    focal = _d(scene["focal"]); size = _d(scene["size"]); sim = _d(scene["sim"])
+    kpo = np.ascontiguousarray(scene["kp_offset"], dtype=np.uint64)
+    kp = np.ascontiguousarray(scene["kp"], dtype=np.float32)
+    pv = np.ascontiguousarray(scene["pair_views"], dtype=np.uint32)
+    mo = np.ascontiguousarray(scene["m_offset"], dtype=np.uint64)
+    mt = np.ascontiguousarray(scene["matches"], dtype=np.uint32)
+    h = L.pgo_run_scene(C.c_uint64(len(focal)), _p(focal, _dp), _p(size, _dp), _p(sim, _dp), _p(kpo, _u64p),
+                        _p(kp, _fp), C.c_uint64(len(pv)), _p(pv, _u32p), _p(mo, _u64p), _p(mt, _u32p),
+                        C.c_double(sim_threshold), C.c_double(thr_px), C.c_uint64(min_inliers), C.c_uint64(min_points),
+                        C.c_uint64(max_depth), C.c_double(weight), C.c_int(1 if use_path_finding else 0),
+                        C.c_uint64(max_pairs))
+    h = C.c_void_p(h)
+    n = L.pgo_run_log_count(h)
+    log = np.zeros(n, dtype=PAIRLOG_DTYPE)
+    if n:
+        L.pgo_run_log_copy(h, log.ctypes.data_as(C.c_void_p))
+    stats = np.zeros(7, dtype=np.uint64)
+    L.pgo_run_stats(h, _p(stats, _u64p))
+    L.pgo_run_free(h)
+    keys = ["edges", "path_accepted", "fallback_accepted", "rejected", "skipped", "corr_evals", "fallback_runs"]
+    return log, dict(zip(keys, (int(s) for s in stats)))
