@@ -1,0 +1,110 @@
+/*
+ * pgb.h — C-ABI of the host side that drives the hypothesis-verification engine (pgi.h): the
+ * similarity-ordered pair queue, the growing pose graph, the visibility table, the A* path search and
+ * the sequential graph commit of the reference, re-organised as SPECULATIVE WAVES with exact validation
+ * so the committed pose graph is identical to the reference's sequential (core_number = 1) result
+ * (SURVEY §7 hard part 3, §8b).
+ *
+ * Reference (citations into /root/reference/src/pyposegraphbuilder/include/):
+ *   PoseGraphBuilder::processImages       pose_graph_builder.h:352-715   (loop order, commit :645-654, :692)
+ *   PoseGraphBuilder::findPath            pose_graph_builder.h:785-862
+ *   AStarTraversal::getPath / recoverPath graph_traversal.h:679-870, :290-348
+ *   SimilarityTable (queue)               imagesimilarity_graph.h:51-66, :108-171
+ *   PoseGraph / VisibilityTable           pose_graph.h:136-224, visibility_table.h:45-171
+ *
+ * Protocol per wave (all ranks of a multi-GPU job run it identically — SPMD host):
+ *   n  = pgb_next_wave(b, max, items)        speculative A* on the current graph snapshot
+ *   ... engine verifies items[i] with need_gpu != 0 (sharded by pair owner, verdicts all-gathered) ...
+ *   pgb_commit_wave(b, verdicts, n_verdicts) sequential commit in queue order; the first item whose
+ *                                            speculation no longer holds and whose verdict is unknown
+ *                                            stops the commit; it and its successors are re-queued.
+ */
+#ifndef PGB_H_
+#define PGB_H_
+
+#include <stdint.h>
+
+#include "pgi.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pgb_builder pgb_builder;
+
+typedef struct pgb_config {
+    double similarity_threshold;         /* cpp_example.cpp:40  (0.5)  */
+    uint64_t minimum_inlier_number;      /* cpp_example.cpp:44  (20)   */
+    uint64_t minimum_point_number;       /* cpp_example.cpp:46  (50)   */
+    uint64_t maximum_search_depth;       /* cpp_example.cpp:54  (5)    */
+    double traversal_heuristics_weight;  /* cpp_example.cpp:50  (0.8)  */
+    int32_t use_path_finding;            /* cpp_example.cpp:36  (true) */
+    int32_t host_threads;                /* threads for the speculative A* (core_number analogue) */
+    int32_t lazy_fallback;               /* 1: waves carry PATH|FALLBACK; 0: fallback verdicts are prefetched */
+    int32_t reserved;
+} pgb_config;
+
+typedef struct pgb_item {
+    uint32_t pair_id;   /* index into the registered pair list                              */
+    uint32_t src, dst;  /* views                                                            */
+    uint8_t has_hyp;    /* A* composed a hypothesis (graph_traversal.h:766-797)             */
+    uint8_t need_gpu;   /* 1: engine must verify this item (verdict not cached)             */
+    uint8_t visible;    /* visibilityTable.hasLink at speculation time                      */
+    uint8_t pad;
+    double hyp[7];      /* qx qy qz qw tx ty tz                                             */
+} pgb_item;
+
+typedef struct pgb_edge {
+    uint32_t src, dst;
+    double q[4], t[3];
+    double score;         /* inlierNumber / matches.size()  pose_graph_builder.h:645-646    */
+    uint32_t inlier_number, n_corr;
+    uint8_t branch, pad[7];
+} pgb_edge;
+
+typedef struct pgb_log {  /* one record per pair popped from the queue, in processing order */
+    uint32_t src, dst;
+    int64_t pair_index;
+    uint8_t visible, had_path, test_passed, branch, committed, pad[3];
+    uint32_t test_count, inlier_number, n_corr, touched_nodes;
+    double E[9], q[4], t[3], score;
+} pgb_log;
+
+typedef struct pgb_counters {
+    uint64_t pairs_popped, committed, path_accepted, fallback_accepted, rejected, skipped;
+    uint64_t waves, items_speculated, items_requeued, astar_runs, astar_reruns, verdict_cache_hits;
+    double sec_astar, sec_commit, sec_visibility;
+} pgb_counters;
+
+/* sim: V x V row-major similarity matrix (the text file of imagesimilarity_graph.h:108-171 already parsed).
+ * pair_views/m_offset describe the pairs that have correspondences (pair id = row). */
+int32_t pgb_create(const pgb_config *cfg, uint64_t n_views, const double *sim, uint64_t n_pairs,
+                   const uint32_t *pair_views, const uint64_t *m_offset, pgb_builder **out);
+void pgb_destroy(pgb_builder *b);
+
+/* Number of queued pairs not yet committed/rejected (0 = done). */
+uint64_t pgb_remaining(pgb_builder *b);
+
+/* Install prefetched fallback verdicts (one per registered pair, index = pair id). */
+int32_t pgb_set_fallback_verdicts(pgb_builder *b, const pgi_verdict *verdicts, uint64_t n_pairs);
+
+/* Pop up to max_items pairs in queue order, run the speculative A* and emit them. Returns the item count. */
+uint32_t pgb_next_wave(pgb_builder *b, uint32_t max_items, pgb_item *items);
+
+/* verdicts: one per item with need_gpu != 0, in item order.  Returns the number of items committed
+ * (accepted, rejected or skipped); the rest were re-queued. */
+uint32_t pgb_commit_wave(pgb_builder *b, const pgi_verdict *verdicts, uint32_t n_verdicts);
+
+uint64_t pgb_edge_count(pgb_builder *b);
+void pgb_copy_edges(pgb_builder *b, pgb_edge *out);
+uint64_t pgb_log_count(pgb_builder *b);
+void pgb_copy_log(pgb_builder *b, pgb_log *out);
+void pgb_get_counters(pgb_builder *b, pgb_counters *out);
+
+/* Stand-alone A* on the builder's current graph (testing). Returns 1 if a hypothesis was composed. */
+int32_t pgb_astar(pgb_builder *b, uint32_t src, uint32_t dst, double *hyp_q_t, uint32_t *touched_nodes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGB_H_ */

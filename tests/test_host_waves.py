@@ -1,0 +1,111 @@
+"""Host logic on CPU: the speculative-wave host (pgb.h) must commit exactly the graph the sequential oracle
+host commits — same edges in the same order with bit-identical poses/scores, same per-pair log — whatever the
+wave size, and with lazy or prefetched fallback verdicts.  Verdicts come from the oracle here (tests only);
+the GPU engine is substituted in tests/test_gpu_scene.py."""
+import numpy as np
+import pytest
+
+from oracle_engine import OracleEngine
+from pose_graph_initialization_b200 import builder as B
+from pose_graph_initialization_b200 import scene as S
+
+CFG = dict(similarity_threshold=0.0, minimum_inlier_number=20, minimum_point_number=50, maximum_search_depth=5,
+           traversal_heuristics_weight=0.8, use_path_finding=True)
+
+
+@pytest.fixture(scope="module")
+def small_scene():
+    return S.make_scene(n_views=12, n_corr=200, outlier_ratio=0.3, seed=5, n_points=700)
+
+
+@pytest.fixture(scope="module")
+def oracle_run(oracle, small_scene):
+    return oracle.run_scene(small_scene, sim_threshold=0.0)
+
+
+def drive(host, eng, wave, lazy):
+    while host.remaining() > 0:
+        items = host.next_wave(wave)
+        todo = items[items["need_gpu"] > 0]
+        v = eng.run_items(todo, path=True, fallback=lazy)
+        host.commit_wave(v)
+
+
+def compare_logs(plog, olog):
+    assert len(plog) == len(olog)
+    for f in ("src", "dst", "pairIndex", "visible", "hadPath", "testPassed", "branch", "committed", "testCount",
+              "inlierNumber", "nCorr", "touchedNodes"):
+        assert np.array_equal(plog[f], olog[f]), f
+    for f in ("E", "q", "t", "score"):
+        assert np.array_equal(plog[f], olog[f]), f
+
+
+@pytest.mark.parametrize("wave,lazy", [(1, True), (7, True), (64, True), (16, False), (1000, False)])
+def test_wave_host_matches_sequential_oracle(oracle, small_scene, oracle_run, wave, lazy):
+    olog, ostats = oracle_run
+    eng = OracleEngine(oracle, small_scene)
+    host = B.HostBuilder(small_scene, host_threads=4, lazy_fallback=lazy, **CFG)
+    if not lazy:
+        fb = np.zeros(host.n_pairs, dtype=B.VERDICT_DTYPE)
+        for p in range(host.n_pairs):
+            fb[p] = eng.verdict(p, None, path=False, fallback=True)
+        host.set_fallback_verdicts(fb)
+    drive(host, eng, wave, lazy)
+    compare_logs(host.log(), olog)
+    edges = host.edges()
+    assert len(edges) == ostats["edges"]
+    committed = olog[olog["committed"] > 0]
+    assert np.array_equal(edges["src"], committed["src"]) and np.array_equal(edges["dst"], committed["dst"])
+    assert np.array_equal(edges["q"], committed["q"]) and np.array_equal(edges["score"], committed["score"])
+    c = host.counters()
+    assert c["committed"] == ostats["edges"] and c["path_accepted"] == ostats["path_accepted"]
+
+
+def test_astar_tie_breaking_matches_oracle_on_tied_similarities(oracle):
+    # coarse similarities (1 decimal) => many equal costs: the heap tie order must be inherited exactly
+    sc = S.make_scene(n_views=10, n_corr=120, outlier_ratio=0.2, seed=9, n_points=500)
+    sc["sim"] = np.round(sc["sim"], 1)
+    np.fill_diagonal(sc["sim"], 1.0)
+    sc["sim"][sc["sim"] >= 1.0] = 0.9
+    np.fill_diagonal(sc["sim"], 1.0)
+    olog, _ = oracle.run_scene(sc, sim_threshold=0.0)
+    eng = OracleEngine(oracle, sc)
+    host = B.HostBuilder(sc, host_threads=2, lazy_fallback=True, **CFG)
+    drive(host, eng, 5, True)
+    compare_logs(host.log(), olog)
+
+
+def test_pairs_without_matches_and_small_pairs_are_skipped(oracle):
+    sc = S.make_scene(n_views=8, n_corr=60, outlier_ratio=0.2, seed=2, n_points=400)
+    # drop some pairs from the pair list (queued by similarity but no correspondences) and shrink one below 50
+    keep = np.ones(len(sc["pair_views"]), dtype=bool)
+    keep[[3, 10]] = False
+    n = 60
+    mo = [0]
+    rows = []
+    for p in range(len(keep)):
+        if not keep[p]:
+            continue
+        m = sc["matches"][p * n:(p + 1) * n]
+        if p == 5:
+            m = m[:40]
+        rows.append(m)
+        mo.append(mo[-1] + len(m))
+    sc["pair_views"] = sc["pair_views"][keep]
+    sc["matches"] = np.vstack(rows)
+    sc["m_offset"] = np.array(mo, dtype=np.uint64)
+    olog, ostats = oracle.run_scene(sc, sim_threshold=0.0)
+    eng = OracleEngine(oracle, sc)
+    host = B.HostBuilder(sc, host_threads=1, lazy_fallback=True, **CFG)
+    drive(host, eng, 9, True)
+    compare_logs(host.log(), olog)
+    assert host.counters()["skipped"] == ostats["skipped"] == 3
+
+
+def test_similarity_threshold_filters_queue(oracle, small_scene):
+    olog, _ = oracle.run_scene(small_scene, sim_threshold=0.6, max_pairs=0)
+    eng = OracleEngine(oracle, small_scene)
+    cfg = dict(CFG, similarity_threshold=0.6)
+    host = B.HostBuilder(small_scene, host_threads=1, lazy_fallback=True, **cfg)
+    drive(host, eng, 8, True)
+    compare_logs(host.log(), olog)
