@@ -73,6 +73,7 @@ typedef struct pgb_log {  /* one record per pair popped from the queue, in proce
 typedef struct pgb_counters {
     uint64_t pairs_popped, committed, path_accepted, fallback_accepted, rejected, skipped;
     uint64_t waves, items_speculated, items_requeued, astar_runs, astar_reruns, verdict_cache_hits;
+    uint64_t astar_pops, astar_pushes; /* heap traffic of all searches (touched nodes / pushed nodes) */
     double sec_astar, sec_commit, sec_visibility;
 } pgb_counters;
 

@@ -42,7 +42,7 @@ class PgbConfig(C.Structure):
 class PgbCounters(C.Structure):
     _fields_ = [(k, C.c_uint64) for k in ("pairs_popped", "committed", "path_accepted", "fallback_accepted", "rejected",
                                           "skipped", "waves", "items_speculated", "items_requeued", "astar_runs",
-                                          "astar_reruns", "verdict_cache_hits")] + \
+                                          "astar_reruns", "verdict_cache_hits", "astar_pops", "astar_pushes")] + \
                [(k, C.c_double) for k in ("sec_astar", "sec_commit", "sec_visibility")]
 
     def as_dict(self):
@@ -218,7 +218,7 @@ class PoseGraphBuilder:
                  kTraversalHeuristicsWeight_=0.8, kSimilarityThreshold_=0.5, kInlierOutlierThreshold_=0.4,
                  kImagePath_="", kWorkspacePath_="", kSimilarityGraphPath_="", kFocalLengthPath_="",
                  kUsePathFinding_=True, kUseGPU_=True, kUseEpipolarHashing_=False, *, scene=None, device=0,
-                 wave_size=256, prefetch_fallback=True, fallback_wave=2048, group=None, rank=0, world_size=1):
+                 wave_size=1024, prefetch_fallback=True, fallback_wave=2048, group=None, rank=0, world_size=1):
         if not kUseGPU_:
             raise ValueError("the B200 path has no CPU implementation (kUseGPU_ must be true)")
         if kUseEpipolarHashing_:
@@ -287,9 +287,8 @@ class PoseGraphBuilder:
             self._prefetch(host)
         t_pre = time.perf_counter()
         flags = WAVE_PATH if self.prefetch_fallback else (WAVE_PATH | WAVE_FALLBACK)
-        wave = self.wave_size
         while host.remaining() > 0:
-            items = host.next_wave(wave)
+            items = host.next_wave(self.wave_size)
             todo = np.nonzero(items["need_gpu"])[0]
             verdicts = np.zeros(len(todo), dtype=VERDICT_DTYPE)
             if len(todo):
@@ -308,12 +307,7 @@ class PoseGraphBuilder:
                 parts = self._exchange(local, counts)
                 for r in range(self.world):
                     verdicts[np.nonzero(own == r)[0]] = parts[r]
-            done = host.commit_wave(verdicts)
-            # adapt the speculation depth to the observed valid prefix
-            if done < len(items) // 2:
-                wave = max(16, wave // 2)
-            elif done == len(items):
-                wave = min(self.wave_size, wave * 2)
+            host.commit_wave(verdicts)  # 0 while the wave still iterates towards its fixed point
         t_end = time.perf_counter()
         self.timing = dict(register_s=t_reg - t0, prefetch_s=t_pre - t_reg, waves_s=t_end - t_pre, total_s=t_end - t0)
         edges = host.edges()

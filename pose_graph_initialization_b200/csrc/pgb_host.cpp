@@ -1,14 +1,22 @@
 // pgb_host.cpp — host side of the B200 path (include/pgb.h): similarity queue, pose graph, visibility
 // table, A* and the sequential commit of the reference, reorganised as speculative waves.
 //
-// Exactness argument (SURVEY §7 hard part 3): the only graph reads of AStarTraversal::getPath are
-// getEdgesByVertex(v) for every EXPANDED vertex v (graph_traversal.h:817) and the (immutable) edges of the
-// found path (graph_traversal.h:323-328).  Committing an edge (u,v) only appends to the edge lists of u
-// and v.  Every vertex carries the commit stamp of its last modification; a speculative search made at
-// stamp s is still what the sequential reference would compute at commit time iff no expanded vertex has a
-// stamp > s and the hasLink answer is unchanged (hasLink is monotone false->true).  Otherwise the search is
-// re-run on the exact sequential state; if it yields a different hypothesis whose verdict is not cached the
-// commit stops there and the rest of the wave is re-queued in order.
+// Wave scheme (exact; SURVEY §7 hard part 3).  A wave is the next W pairs of the queue, positions 0..W-1.
+//   * Every position k carries a PREDICTED verdict pv_k (initially the pair's hypothesis-independent fallback
+//     verdict, which is prefetched).  The accepted predictions form an OVERLAY on the committed graph: an
+//     append-only per-vertex edge list tagged with the position that adds the edge, plus a sequentially
+//     simulated visibility table.  The search of position k sees the committed graph plus overlay entries of
+//     positions < k — i.e. exactly the graph the sequential reference would have IF the predictions hold.
+//   * All positions are searched in parallel (thread pool), the engine verifies the (pair, hypothesis) tuples,
+//     the actual verdicts a_k replace the predictions where they differ (a path hypothesis was accepted), and
+//     only the positions whose search READ something that changed are searched again: the only graph reads of
+//     AStarTraversal::getPath are getEdgesByVertex(v) for every EXPANDED vertex v (graph_traversal.h:817) and
+//     the edges of the found path (graph_traversal.h:323-328), so position m is stale iff an expanded vertex of
+//     m is an endpoint of a changed position k < m, or its hasLink answer changed.
+//   * Position 0 depends on nothing in the wave, so by induction the iteration reaches the fixed point
+//     "h_k == A*(graph after the actual verdicts of positions < k) for every k", which IS the sequential
+//     semantics; the whole wave is then committed in order.  (pair, hypothesis) -> verdict is a pure function and
+//     is cached, so a re-searched position only costs engine work when its hypothesis really changed.
 //
 // Data structures are flat (arena A* nodes, bit-matrix visibility, per-vertex edge index vectors) but the
 // heap is driven by the same std::push_heap/std::pop_heap calls std::priority_queue makes, so ties break
@@ -19,7 +27,10 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <condition_variable>
 #include <deque>
+#include <functional>
+#include <mutex>
 #include <queue>
 #include <thread>
 #include <tuple>
@@ -86,9 +97,14 @@ struct Edge {
 
 inline uint64_t edgeKey(uint32_t s, uint32_t d) { return ((uint64_t)s << 32) | d; }
 
+struct Adj {  // one entry of a vertex' edge list, flattened for the A* inner loop
+    uint32_t next;   // the other endpoint (graph_traversal.h:838-840)
+    uint32_t edge;
+    double score;
+};
 struct Graph {
     std::vector<Edge> edges;                       // commit order (= PoseGraph::edges_ids)
-    std::vector<std::vector<uint32_t>> byVertex;   // edge indices per vertex in insertion order (pose_graph.h:219-220)
+    std::vector<std::vector<Adj>> byVertex;        // per-vertex edge list in insertion order (pose_graph.h:219-220)
     std::unordered_map<uint64_t, uint32_t> lookup; // (src,dst) -> edge index
     bool hasEdge(uint32_t s, uint32_t d) const { return lookup.find(edgeKey(s, d)) != lookup.end(); }
     const Edge *find(uint32_t s, uint32_t d) const
@@ -161,6 +177,7 @@ struct AStarOut {
     bool found = false;
     SE3 pose = se3Identity();
     uint32_t touched = 0;
+    uint32_t pushes = 0;
     std::vector<uint32_t> expanded;  // vertices whose edge lists were read
 };
 
@@ -181,12 +198,61 @@ struct AStarScratch {
     std::vector<uint32_t> path;
 };
 
+// Predicted edges of the open wave, layered over the committed graph.
+struct OvAdj {
+    Adj a;
+    uint32_t pos;  // wave position that adds the edge
+};
+struct Overlay {
+    std::vector<std::vector<OvAdj>> byVertex;        // appended in position order
+    std::vector<Edge> edges;                         // index = Adj::edge - kOverlayBase
+    std::vector<uint32_t> edgePos;
+    std::unordered_map<uint64_t, uint32_t> lookup;   // (src,dst) -> overlay edge index
+    std::vector<uint32_t> touchedVertices;
+    void clear()
+    {
+        for (uint32_t v : touchedVertices) byVertex[v].clear();
+        touchedVertices.clear();
+        edges.clear();
+        edgePos.clear();
+        lookup.clear();
+    }
+    void add(const Edge &e, uint32_t pos)
+    {
+        const uint32_t ei = (uint32_t)edges.size();
+        edges.push_back(e);
+        edgePos.push_back(pos);
+        lookup[edgeKey(e.src, e.dst)] = ei;
+        if (byVertex[e.src].empty()) touchedVertices.push_back(e.src);
+        byVertex[e.src].push_back(OvAdj{Adj{e.dst, ei, e.score}, pos});
+        if (byVertex[e.dst].empty()) touchedVertices.push_back(e.dst);
+        byVertex[e.dst].push_back(OvAdj{Adj{e.src, ei, e.score}, pos});
+    }
+};
+
+struct GraphView {
+    const Graph *g;
+    const Overlay *ov;  // may be null
+    uint32_t cutoff;    // overlay entries with pos < cutoff are visible
+    const Edge *find(uint32_t s, uint32_t d) const
+    {
+        if (const Edge *e = g->find(s, d)) return e;
+        if (ov) {
+            auto it = ov->lookup.find(edgeKey(s, d));
+            if (it != ov->lookup.end() && ov->edgePos[it->second] < cutoff) return &ov->edges[it->second];
+        }
+        return nullptr;
+    }
+};
+
 // AStarTraversal<ImageSimilarityHeuristics>::getPath with the arguments of pose_graph_builder.h:834-841.
-void aStar(const Graph &g, const double *sim, uint32_t V, uint32_t from, uint32_t to, size_t maxDepth, double weight,
-           AStarScratch &S, AStarOut &out)
+void aStar(const GraphView &gv, const double *sim /*transposed*/, uint32_t V, uint32_t from, uint32_t to, size_t maxDepth,
+           double weight, AStarScratch &S, AStarOut &out)
 {
+    const Graph &g = *gv.g;
     out.found = false;
     out.touched = 0;
+    out.pushes = 0;
     out.expanded.clear();
     if (S.mark.size() != V) { S.mark.assign(V, 0); S.epoch = 0; }
     if (++S.epoch == 0) { std::fill(S.mark.begin(), S.mark.end(), 0); S.epoch = 1; }
@@ -197,7 +263,11 @@ void aStar(const Graph &g, const double *sim, uint32_t V, uint32_t from, uint32_
     S.heap.push_back(HeapItem{0.0, 0});
     std::push_heap(S.heap.begin(), S.heap.end(), cmp);
     const double oneMinusWeight = 1.0 - weight;
-    const std::vector<uint32_t> *edges = nullptr;  // `edges` keeps its previous content if the vertex has none (pose_graph.h:145-146)
+    // `edges` keeps its previous content when a vertex has no list (pose_graph.h:145-146).  Every vertex reached by
+    // the search has at least the edge it was reached through, and the source has edges whenever hasLink holds, so
+    // the stale case cannot occur; the owner is tracked only to keep the restatement literal.
+    uint32_t listOwner = UINT32_MAX;
+    const double *simTo = sim + (size_t)to * V;  // transposed table: simTo[next] = similarity(next, to)
     while (!S.heap.empty()) {
         const uint32_t ni = S.heap.front().node;
         ++out.touched;  // :750
@@ -214,9 +284,9 @@ void aStar(const Graph &g, const double *sim, uint32_t V, uint32_t from, uint32_
             bool ok = true;
             for (size_t i = 1; i < S.path.size(); ++i) {
                 const uint32_t s = S.path[i - 1], d = S.path[i];
-                if (const Edge *e = g.find(s, d))
+                if (const Edge *e = gv.find(s, d))
                     pose = se3Mul(e->T, pose);  // :344
-                else if (const Edge *e2 = g.find(d, s))
+                else if (const Edge *e2 = gv.find(d, s))
                     pose = se3Mul(se3Inverse(e2->T), pose);  // :342
                 else { ok = false; break; }
             }
@@ -229,14 +299,18 @@ void aStar(const Graph &g, const double *sim, uint32_t V, uint32_t from, uint32_
         }
         S.mark[v] = S.epoch;  // nodeStates[v] = Open  :814
         out.expanded.push_back(v);
-        if (!g.byVertex[v].empty()) edges = &g.byVertex[v];  // :817
-        if (node.depth < maxDepth && edges) {  // :820
-            for (uint32_t ei : *edges) {
-                const Edge &e = g.edges[ei];
-                if (e.score < 0.0) continue;  // kMinimumInlierRatio is `const bool` receiving 0.0 (:613, :839)
-                const uint32_t next = (v == e.dst) ? e.src : e.dst;  // :838-840
+        const std::vector<Adj> &real = g.byVertex[v];
+        const std::vector<OvAdj> *ovl = gv.ov ? &gv.ov->byVertex[v] : nullptr;
+        const bool hasOv = ovl && !ovl->empty() && (*ovl)[0].pos < gv.cutoff;
+        if (!real.empty() || hasOv) listOwner = v;  // :817
+        if (node.depth < maxDepth && listOwner != UINT32_MAX) {  // :820
+            const uint32_t lv = listOwner;
+            auto visit = [&](const Adj &e) {
+                if (e.score < 0.0) return;  // kMinimumInlierRatio is `const bool` receiving 0.0 (:613, :839)
+                uint32_t next = e.next;     // (v == dst) ? src : dst  :838-840
+                if (lv != v) next = e.next == v ? lv : e.next;  // stale list of another vertex (unreachable, see above)
                 const double edgeCost = node.c0 > e.score ? e.score : node.c0;  // MIN :843
-                double h = sim[(size_t)next * V + to];
+                double h = simTo[next];  // getSimilarity(next, to)
                 h = h < 0.0 ? 0.0 : (1.0 < h ? 1.0 : h);  // std::clamp(similarity, 0, 1)  :594
                 const double nextToDest = node.c1 < h ? h : node.c1;  // MAX :847
                 const double combined = weight * edgeCost + oneMinusWeight * nextToDest;  // :851-852
@@ -244,25 +318,48 @@ void aStar(const Graph &g, const double *sim, uint32_t V, uint32_t from, uint32_
                     S.arena.push_back(ArenaNode{next, ni, node.depth + 1, edgeCost, nextToDest});
                     S.heap.push_back(HeapItem{combined, (uint32_t)S.arena.size() - 1});
                     std::push_heap(S.heap.begin(), S.heap.end(), cmp);
+                    ++out.pushes;
                 }
-            }
+            };
+            for (const Adj &e : g.byVertex[lv]) visit(e);
+            if (gv.ov)
+                for (const OvAdj &oe : gv.ov->byVertex[lv]) {
+                    if (oe.pos >= gv.cutoff) break;
+                    visit(oe.a);
+                }
         }
     }
 }
+
+// What a position contributes to the graph: nothing, or an edge with a pose/score.
+struct Outcome {
+    bool known = false;     // verdict available
+    bool accepted = false;
+    uint8_t branch = 0;
+    uint32_t inliers = 0;
+    double q[4] = {0, 0, 0, 1}, t[3] = {0, 0, 0};
+    bool sameEdge(const Outcome &o) const
+    {
+        if (known != o.known || accepted != o.accepted) return false;
+        if (!accepted) return true;
+        return inliers == o.inliers && !memcmp(q, o.q, sizeof q) && !memcmp(t, o.t, sizeof t);
+    }
+};
 
 struct Item {
     uint32_t pairId = UINT32_MAX;  // UINT32_MAX: queued pair without registered correspondences
     uint32_t src = 0, dst = 0;
     uint32_t nCorr = 0;
-    bool specDone = false;
+    bool staticSkip = false;  // no correspondences / fewer than minimum_point_number (pose_graph_builder.h:550-551)
+    bool searched = false;    // search result below is consistent with the current overlay
     bool visible = false;
     bool hasHyp = false;
     SE3 hyp = se3Identity();
-    uint64_t stamp = 0;  // commit counter when the speculation was made
     std::vector<uint32_t> expanded;
-    uint32_t touched = 0;
+    uint32_t touched = 0, pushes = 0;
     bool needGpu = false;
-    int verdictSlot = -1;
+    Outcome pred;             // what the overlay currently assumes for this position
+    const pgi_verdict *finalV = nullptr, *pathV = nullptr;
 };
 
 struct HypKey {
@@ -294,12 +391,68 @@ inline HypKey makeKey(uint32_t pair, const SE3 &h)
 
 double nowSec() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
+// Minimal persistent worker pool (the reference spawns one OpenMP worker per core, pose_graph_builder.h:391-397).
+struct Pool {
+    std::vector<std::thread> threads;
+    std::mutex m;
+    std::condition_variable cvWork, cvDone;
+    std::function<void(int)> job;
+    uint64_t generation = 0;
+    int active = 0;
+    bool quit = false;
+    void start(int n)
+    {
+        for (int t = 1; t < n; t++)
+            threads.emplace_back([this, t]() {
+                uint64_t seen = 0;
+                for (;;) {
+                    std::function<void(int)> j;
+                    {
+                        std::unique_lock<std::mutex> lk(m);
+                        cvWork.wait(lk, [&]() { return quit || generation != seen; });
+                        if (quit) return;
+                        seen = generation;
+                        j = job;
+                    }
+                    j(t);
+                    {
+                        std::lock_guard<std::mutex> lk(m);
+                        if (--active == 0) cvDone.notify_all();
+                    }
+                }
+            });
+    }
+    void run(const std::function<void(int)> &j)
+    {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            job = j;
+            active = (int)threads.size();
+            ++generation;
+        }
+        cvWork.notify_all();
+        j(0);
+        std::unique_lock<std::mutex> lk(m);
+        cvDone.wait(lk, [&]() { return active == 0; });
+    }
+    ~Pool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            quit = true;
+        }
+        cvWork.notify_all();
+        for (auto &t : threads) t.join();
+    }
+};
+
 }  // namespace
 
 struct pgb_builder {
     pgb_config cfg;
+    Pool pool;
     uint32_t V = 0;
-    std::vector<double> sim;
+    std::vector<double> sim;  // transposed
     uint64_t P = 0;
     std::vector<uint32_t> pairViews;
     std::vector<uint64_t> mOffset;
@@ -309,10 +462,12 @@ struct pgb_builder {
     size_t nextInOrder = 0;
     std::deque<Item> pending;  // re-queued items, in queue order, ahead of `order[nextInOrder..]`
     Graph graph;
-    Visibility vis;
-    std::vector<uint64_t> vertexStamp;
-    uint64_t commitStamp = 0;
+    Visibility vis, visPred;
+    Overlay overlay;
     std::vector<Item> wave;
+    bool waveOpen = false;
+    int rounds = 0;
+    std::vector<uint32_t> minChangedPos;  // per vertex: smallest wave position whose outcome changed this round
     std::vector<pgi_verdict> fbCache;
     std::vector<uint8_t> fbHave;
     std::unordered_map<HypKey, PathVerdict, HypKeyHash> pathCache;
@@ -323,44 +478,205 @@ struct pgb_builder {
 
 namespace {
 
-void speculate(pgb_builder *b, Item &it, AStarScratch &S)
+Outcome outcomeOf(const pgi_verdict *v)
 {
-    it.visible = b->vis.hasLink(it.src, it.dst);  // pose_graph_builder.h:456-457
+    Outcome o;
+    o.known = v != nullptr;
+    if (v && v->accepted) {
+        o.accepted = true;
+        o.branch = v->branch;
+        o.inliers = v->inlier_count;
+        memcpy(o.q, v->q, sizeof o.q);
+        memcpy(o.t, v->t, sizeof o.t);
+    }
+    return o;
+}
+
+Edge edgeOf(const Item &it, const Outcome &o)
+{
+    Edge e;
+    e.src = it.src; e.dst = it.dst;
+    memcpy(e.T.q, o.q, 32);
+    memcpy(e.T.t, o.t, 24);
+    e.score = (double)o.inliers / (double)it.nCorr;  // pose_graph_builder.h:645-646
+    e.inlierNumber = o.inliers; e.nCorr = it.nCorr; e.branch = o.branch;
+    return e;
+}
+
+// Rebuild the overlay and the simulated visibility from the current predictions; positions whose hasLink answer
+// changed lose their search result.
+void rebuildOverlay(pgb_builder *b)
+{
+    const double t0 = nowSec();
+    b->overlay.clear();
+    b->visPred = b->vis;
+    for (uint32_t k = 0; k < b->wave.size(); k++) {
+        Item &it = b->wave[k];
+        const bool vis = b->visPred.hasLink(it.src, it.dst);  // pose_graph_builder.h:456-457 at position k
+        if (it.searched && vis != it.visible) it.searched = false;
+        it.visible = vis;
+        if (!it.staticSkip && it.pred.known && it.pred.accepted) {
+            b->overlay.add(edgeOf(it, it.pred), k);
+            b->visPred.addLink(it.src, it.dst);  // :692
+        }
+    }
+    b->ctr.sec_visibility += nowSec() - t0;
+}
+
+void searchPosition(pgb_builder *b, uint32_t k, AStarScratch &S)
+{
+    Item &it = b->wave[k];
     it.hasHyp = false;
     it.expanded.clear();
-    it.touched = 0;
-    it.stamp = b->commitStamp;
-    if (b->cfg.use_path_finding && it.visible && it.pairId != UINT32_MAX && it.nCorr >= b->cfg.minimum_point_number) {
+    it.touched = it.pushes = 0;
+    if (b->cfg.use_path_finding && it.visible && !it.staticSkip) {  // :569-570
         AStarOut o;
-        aStar(b->graph, b->sim.data(), b->V, it.src, it.dst, (size_t)b->cfg.maximum_search_depth,
+        GraphView gv{&b->graph, &b->overlay, k};
+        aStar(gv, b->sim.data(), b->V, it.src, it.dst, (size_t)b->cfg.maximum_search_depth,
               b->cfg.traversal_heuristics_weight, S, o);
         it.hasHyp = o.found;
         it.hyp = o.pose;
         it.expanded.swap(o.expanded);
         it.touched = o.touched;
+        it.pushes = o.pushes;
     }
-    it.specDone = true;
+    it.searched = true;
 }
 
-bool speculationHolds(const pgb_builder *b, const Item &it)
+void searchStale(pgb_builder *b)
 {
-    if (!it.specDone) return false;
-    if (!it.visible && b->vis.hasLink(it.src, it.dst)) return false;
-    for (uint32_t v : it.expanded)
-        if (b->vertexStamp[v] > it.stamp) return false;
-    return true;
+    const double t0 = nowSec();
+    std::vector<uint32_t> todo;
+    for (uint32_t k = 0; k < b->wave.size(); k++)
+        if (!b->wave[k].searched) todo.push_back(k);
+    if (b->cfg.host_threads <= 1 || todo.size() < 4) {
+        for (uint32_t k : todo) searchPosition(b, k, b->scratch[0]);
+    } else {
+        std::atomic<size_t> next(0);
+        b->pool.run([&](int tid) {
+            for (;;) {
+                const size_t i = next.fetch_add(1);
+                if (i >= todo.size()) break;
+                searchPosition(b, todo[i], b->scratch[tid]);
+            }
+        });
+    }
+    for (uint32_t k : todo) { b->ctr.astar_pops += b->wave[k].touched; b->ctr.astar_pushes += b->wave[k].pushes; }
+    b->ctr.astar_runs += todo.size();
+    if (b->rounds > 0) b->ctr.astar_reruns += todo.size();
+    b->ctr.sec_astar += nowSec() - t0;
 }
 
-bool needsGpu(const pgb_builder *b, const Item &it)
+// Resolve the verdict of every position from the caches.  Returns the number of positions that need the engine.
+uint32_t resolveVerdicts(pgb_builder *b)
 {
-    if (it.pairId == UINT32_MAX || it.nCorr < b->cfg.minimum_point_number) return false;
-    if (b->graph.hasEdge(it.src, it.dst) || b->graph.hasEdge(it.dst, it.src)) return false;
-    if (it.hasHyp) {
-        auto pc = b->pathCache.find(makeKey(it.pairId, it.hyp));
-        if (pc == b->pathCache.end()) return true;
-        if (pc->second.ok) return false;
+    uint32_t need = 0;
+    for (Item &it : b->wave) {
+        it.needGpu = false;
+        it.finalV = it.pathV = nullptr;
+        if (it.staticSkip) continue;
+        if (it.hasHyp) {
+            auto pc = b->pathCache.find(makeKey(it.pairId, it.hyp));
+            if (pc == b->pathCache.end()) { it.needGpu = true; ++need; continue; }
+            it.pathV = &pc->second.v;
+            if (pc->second.ok) it.finalV = it.pathV;
+        }
+        if (!it.finalV) {
+            if (!b->fbHave[it.pairId]) { it.needGpu = true; ++need; continue; }
+            it.finalV = &b->fbCache[it.pairId];
+        }
     }
-    return !b->fbHave[it.pairId];
+    return need;
+}
+
+void commitPosition(pgb_builder *b, Item &it)
+{
+    pgb_log lg;
+    memset(&lg, 0, sizeof lg);
+    lg.src = it.src; lg.dst = it.dst;
+    lg.pair_index = it.pairId == UINT32_MAX ? -1 : (int64_t)it.pairId;
+    lg.n_corr = it.nCorr;
+    b->ctr.pairs_popped++;
+    if (b->graph.hasEdge(it.src, it.dst) || b->graph.hasEdge(it.dst, it.src)) {  // pose_graph_builder.h:438-443
+        b->ctr.skipped++;
+        b->log.push_back(lg);
+        return;
+    }
+    lg.visible = it.visible;
+    if (it.staticSkip) {  // :550-551
+        b->ctr.skipped++;
+        b->log.push_back(lg);
+        return;
+    }
+    const pgi_verdict *final = it.finalV;
+    lg.had_path = it.hasHyp;
+    lg.touched_nodes = it.touched;
+    if (it.pathV) { lg.test_passed = it.pathV->test_passed; lg.test_count = it.pathV->test_count; }
+    lg.branch = final->accepted ? final->branch : 0;
+    lg.inlier_number = final->inlier_count;
+    memcpy(lg.E, final->E, sizeof lg.E);
+    if (!final->accepted) {  // :641-642
+        b->ctr.rejected++;
+        b->log.push_back(lg);
+        return;
+    }
+    const Edge e = edgeOf(it, outcomeOf(final));
+    const uint32_t ei = (uint32_t)b->graph.edges.size();
+    b->graph.edges.push_back(e);
+    b->graph.lookup[edgeKey(e.src, e.dst)] = ei;
+    b->graph.byVertex[e.src].push_back(Adj{e.dst, ei, e.score});  // pose_graph.h:219-220
+    b->graph.byVertex[e.dst].push_back(Adj{e.src, ei, e.score});
+    const double tv = nowSec();
+    b->vis.addLink(e.src, e.dst);  // :692
+    b->ctr.sec_visibility += nowSec() - tv;
+    lg.committed = 1;
+    memcpy(lg.q, final->q, 32);
+    memcpy(lg.t, final->t, 24);
+    lg.score = e.score;
+    b->log.push_back(lg);
+    b->ctr.committed++;
+    if (final->branch == 1) b->ctr.path_accepted++; else b->ctr.fallback_accepted++;
+}
+
+// Iterate the open wave towards its fixed point.  Returns the number of positions committed (0 while the wave
+// still waits for engine verdicts).
+uint32_t advanceWave(pgb_builder *b)
+{
+    const uint32_t n = (uint32_t)b->wave.size();
+    for (;;) {
+        searchStale(b);
+        if (resolveVerdicts(b) > 0) return 0;  // engine round trip needed; the wave stays open
+        // actual outcomes vs. the predictions the overlay was built from
+        std::fill(b->minChangedPos.begin(), b->minChangedPos.end(), UINT32_MAX);
+        uint32_t firstChanged = UINT32_MAX;
+        for (uint32_t k = 0; k < n; k++) {
+            Item &it = b->wave[k];
+            if (it.staticSkip) continue;
+            const Outcome act = outcomeOf(it.finalV);
+            if (!act.sameEdge(it.pred)) {
+                it.pred = act;
+                if (firstChanged == UINT32_MAX) firstChanged = k;
+                b->minChangedPos[it.src] = std::min(b->minChangedPos[it.src], k);
+                b->minChangedPos[it.dst] = std::min(b->minChangedPos[it.dst], k);
+            }
+        }
+        if (firstChanged == UINT32_MAX) break;  // fixed point: every search saw exactly the sequential graph
+        ++b->rounds;
+        for (uint32_t m = firstChanged + 1; m < n; m++) {
+            Item &it = b->wave[m];
+            if (!it.searched) continue;
+            for (uint32_t v : it.expanded)
+                if (b->minChangedPos[v] < m) { it.searched = false; break; }
+        }
+        rebuildOverlay(b);
+    }
+    const double t0 = nowSec();
+    for (Item &it : b->wave) commitPosition(b, it);
+    b->wave.clear();
+    b->waveOpen = false;
+    b->overlay.clear();
+    b->ctr.sec_commit += nowSec() - t0;
+    return n;
 }
 
 }  // namespace
@@ -375,7 +691,9 @@ int32_t pgb_create(const pgb_config *cfg, uint64_t n_views, const double *sim, u
     b->cfg = *cfg;
     if (b->cfg.host_threads <= 0) b->cfg.host_threads = (int32_t)std::max(1u, std::thread::hardware_concurrency());
     b->V = (uint32_t)n_views;
-    b->sim.assign(sim, sim + n_views * n_views);
+    b->sim.resize(n_views * n_views);  // stored TRANSPOSED: sim[to * V + next] = similarity(next, to)
+    for (uint64_t r = 0; r < n_views; r++)
+        for (uint64_t c = 0; c < n_views; c++) b->sim[c * n_views + r] = sim[r * n_views + c];
     b->P = n_pairs;
     b->pairViews.assign(pair_views, pair_views + 2 * n_pairs);
     b->mOffset.assign(m_offset, m_offset + n_pairs + 1);
@@ -399,12 +717,14 @@ int32_t pgb_create(const pgb_config *cfg, uint64_t n_views, const double *sim, u
         }
     }
     b->graph.byVertex.resize(n_views);
+    b->overlay.byVertex.resize(n_views);
     b->vis.init((uint32_t)n_views);
-    b->vertexStamp.assign(n_views, 0);
+    b->minChangedPos.assign(n_views, UINT32_MAX);
     b->fbCache.resize(n_pairs);
     b->fbHave.assign(n_pairs, 0);
     memset(&b->ctr, 0, sizeof b->ctr);
     b->scratch.resize(b->cfg.host_threads);
+    b->pool.start(b->cfg.host_threads);
     *out = b;
     return 0;
 }
@@ -423,17 +743,32 @@ int32_t pgb_set_fallback_verdicts(pgb_builder *b, const pgi_verdict *verdicts, u
     return 0;
 }
 
+static uint32_t emitItems(pgb_builder *b, pgb_item *items)
+{
+    const uint32_t n = (uint32_t)b->wave.size();
+    for (uint32_t i = 0; i < n; i++) {
+        const Item &it = b->wave[i];
+        pgb_item &o = items[i];
+        o.pair_id = it.pairId;
+        o.src = it.src; o.dst = it.dst;
+        o.has_hyp = it.hasHyp; o.need_gpu = it.needGpu; o.visible = it.visible; o.pad = 0;
+        memcpy(o.hyp, it.hyp.q, 32);
+        memcpy(o.hyp + 4, it.hyp.t, 24);
+    }
+    return n;
+}
+
 uint32_t pgb_next_wave(pgb_builder *b, uint32_t max_items, pgb_item *items)
 {
-    if (!b || !items || !b->wave.empty()) return 0;
-    const double t0 = nowSec();
-    // 1. gather items in queue order: re-queued ones first, then fresh pops
+    if (!b || !items) return 0;
+    if (b->waveOpen) return emitItems(b, items);  // still waiting for verdicts of the open wave
+    // 1. gather positions in queue order: re-queued ones first, then fresh pops
     while (b->wave.size() < max_items) {
+        Item it;
         if (!b->pending.empty()) {
-            b->wave.push_back(std::move(b->pending.front()));
+            it = std::move(b->pending.front());
             b->pending.pop_front();
         } else if (b->nextInOrder < b->order.size()) {
-            Item it;
             it.src = b->order[b->nextInOrder].first;
             it.dst = b->order[b->nextInOrder].second;
             ++b->nextInOrder;
@@ -442,59 +777,33 @@ uint32_t pgb_next_wave(pgb_builder *b, uint32_t max_items, pgb_item *items)
                 it.pairId = pi->second;
                 it.nCorr = (uint32_t)(b->mOffset[it.pairId + 1] - b->mOffset[it.pairId]);
             }
-            b->wave.push_back(std::move(it));
+            it.staticSkip = it.pairId == UINT32_MAX || it.nCorr < b->cfg.minimum_point_number;
         } else
             break;
+        it.searched = false;
+        // prediction: the pair's hypothesis-independent fallback verdict, if already known
+        const bool fbKnown = !it.staticSkip && b->fbHave[it.pairId];
+        it.pred = fbKnown ? outcomeOf(&b->fbCache[it.pairId]) : Outcome();
+        b->wave.push_back(std::move(it));
+        if (!b->wave.back().staticSkip && !fbKnown) break;  // nothing can be predicted behind an unknown outcome
     }
-    const uint32_t n = (uint32_t)b->wave.size();
-    // 2. (re-)speculate where needed, in parallel on the current snapshot
-    std::vector<uint32_t> todo;
-    for (uint32_t i = 0; i < n; i++)
-        if (!speculationHolds(b, b->wave[i])) todo.push_back(i);
-    b->ctr.astar_runs += todo.size();
-    const int T = std::max(1, std::min<int>(b->cfg.host_threads, (int)((todo.size() + 7) / 8)));
-    if (T <= 1) {
-        for (uint32_t i : todo) speculate(b, b->wave[i], b->scratch[0]);
-    } else {
-        std::atomic<size_t> next(0);
-        auto worker = [&](int tid) {
-            for (;;) {
-                const size_t k = next.fetch_add(1);
-                if (k >= todo.size()) break;
-                speculate(b, b->wave[todo[k]], b->scratch[tid]);
-            }
-        };
-        std::vector<std::thread> pool;
-        for (int t = 1; t < T; t++) pool.emplace_back(worker, t);
-        worker(0);
-        for (auto &th : pool) th.join();
-    }
-    // 3. emit
-    for (uint32_t i = 0; i < n; i++) {
-        Item &it = b->wave[i];
-        it.needGpu = needsGpu(b, it);
-        pgb_item &o = items[i];
-        o.pair_id = it.pairId;
-        o.src = it.src; o.dst = it.dst;
-        o.has_hyp = it.hasHyp; o.need_gpu = it.needGpu; o.visible = it.visible; o.pad = 0;
-        memcpy(o.hyp, it.hyp.q, 32);
-        memcpy(o.hyp + 4, it.hyp.t, 24);
-    }
+    if (b->wave.empty()) return 0;
+    b->waveOpen = true;
+    b->rounds = 0;
     b->ctr.waves++;
-    b->ctr.items_speculated += n;
-    b->ctr.sec_astar += nowSec() - t0;
-    return n;
+    b->ctr.items_speculated += b->wave.size();
+    rebuildOverlay(b);
+    searchStale(b);
+    resolveVerdicts(b);
+    return emitItems(b, items);
 }
 
 uint32_t pgb_commit_wave(pgb_builder *b, const pgi_verdict *verdicts, uint32_t n_verdicts)
 {
-    if (!b) return 0;
-    const double t0 = nowSec();
-    const uint32_t n = (uint32_t)b->wave.size();
+    if (!b || !b->waveOpen) return 0;
     // absorb the engine's verdicts into the caches (pure functions of (pair, hypothesis) / of the pair)
     uint32_t vi = 0;
-    for (uint32_t i = 0; i < n; i++) {
-        Item &it = b->wave[i];
+    for (Item &it : b->wave) {
         if (!it.needGpu) continue;
         if (vi >= n_verdicts || !verdicts) break;
         const pgi_verdict &v = verdicts[vi++];
@@ -509,88 +818,7 @@ uint32_t pgb_commit_wave(pgb_builder *b, const pgi_verdict *verdicts, uint32_t n
             b->fbHave[it.pairId] = 1;
         }
     }
-    uint32_t done = 0;
-    AStarScratch &S = b->scratch[0];
-    for (; done < n; ++done) {
-        Item &it = b->wave[done];
-        pgb_log lg;
-        memset(&lg, 0, sizeof lg);
-        lg.src = it.src; lg.dst = it.dst;
-        lg.pair_index = it.pairId == UINT32_MAX ? -1 : (int64_t)it.pairId;
-        lg.n_corr = it.nCorr;
-        if (b->graph.hasEdge(it.src, it.dst) || b->graph.hasEdge(it.dst, it.src)) {  // pose_graph_builder.h:438-443
-            b->ctr.skipped++;
-            b->ctr.pairs_popped++;
-            b->log.push_back(lg);
-            continue;
-        }
-        if (!speculationHolds(b, it)) {  // exact sequential state: re-run (this IS the reference's search)
-            speculate(b, it, S);
-            b->ctr.astar_reruns++;
-        }
-        lg.visible = it.visible;
-        if (it.pairId == UINT32_MAX || it.nCorr < b->cfg.minimum_point_number) {  // :550-551
-            b->ctr.skipped++;
-            b->ctr.pairs_popped++;
-            b->log.push_back(lg);
-            continue;
-        }
-        // resolve the verdict of (pair, exact hypothesis)
-        const pgi_verdict *final = nullptr;
-        const pgi_verdict *pathV = nullptr;
-        if (it.hasHyp) {
-            auto pc = b->pathCache.find(makeKey(it.pairId, it.hyp));
-            if (pc == b->pathCache.end()) break;  // unknown: re-queue from here
-            pathV = &pc->second.v;
-            if (pc->second.ok) final = pathV;
-        }
-        if (!final) {
-            if (!b->fbHave[it.pairId]) break;
-            final = &b->fbCache[it.pairId];
-        }
-        lg.had_path = it.hasHyp;
-        lg.touched_nodes = it.touched;
-        if (pathV) { lg.test_passed = pathV->test_passed; lg.test_count = pathV->test_count; }
-        lg.branch = final->accepted ? final->branch : 0;
-        lg.inlier_number = final->inlier_count;
-        memcpy(lg.E, final->E, sizeof lg.E);
-        b->ctr.pairs_popped++;
-        if (!final->accepted) {  // :641-642
-            b->ctr.rejected++;
-            b->log.push_back(lg);
-            continue;
-        }
-        Edge e;
-        e.src = it.src; e.dst = it.dst;
-        memcpy(e.T.q, final->q, 32);
-        memcpy(e.T.t, final->t, 24);
-        e.score = (double)final->inlier_count / (double)it.nCorr;  // :645-646
-        e.inlierNumber = final->inlier_count; e.nCorr = it.nCorr; e.branch = final->branch;
-        const uint32_t ei = (uint32_t)b->graph.edges.size();
-        b->graph.edges.push_back(e);
-        b->graph.lookup[edgeKey(e.src, e.dst)] = ei;
-        b->graph.byVertex[e.src].push_back(ei);  // pose_graph.h:219-220
-        b->graph.byVertex[e.dst].push_back(ei);
-        ++b->commitStamp;
-        b->vertexStamp[e.src] = b->commitStamp;
-        b->vertexStamp[e.dst] = b->commitStamp;
-        const double tv = nowSec();
-        b->vis.addLink(e.src, e.dst);  // :692
-        b->ctr.sec_visibility += nowSec() - tv;
-        lg.committed = 1;
-        memcpy(lg.q, final->q, 32);
-        memcpy(lg.t, final->t, 24);
-        lg.score = e.score;
-        b->log.push_back(lg);
-        b->ctr.committed++;
-        if (final->branch == 1) b->ctr.path_accepted++; else b->ctr.fallback_accepted++;
-    }
-    // re-queue the tail in order
-    for (uint32_t i = n; i > done; --i) b->pending.push_front(std::move(b->wave[i - 1]));
-    b->ctr.items_requeued += n - done;
-    b->wave.clear();
-    b->ctr.sec_commit += nowSec() - t0;
-    return done;
+    return advanceWave(b);
 }
 
 uint64_t pgb_edge_count(pgb_builder *b) { return b ? b->graph.edges.size() : 0; }
@@ -614,7 +842,8 @@ int32_t pgb_astar(pgb_builder *b, uint32_t src, uint32_t dst, double *hyp_q_t, u
 {
     if (!b || src >= b->V || dst >= b->V) return -1;
     AStarOut o;
-    aStar(b->graph, b->sim.data(), b->V, src, dst, (size_t)b->cfg.maximum_search_depth, b->cfg.traversal_heuristics_weight,
+    GraphView gv{&b->graph, nullptr, 0};
+    aStar(gv, b->sim.data(), b->V, src, dst, (size_t)b->cfg.maximum_search_depth, b->cfg.traversal_heuristics_weight,
           b->scratch[0], o);
     if (hyp_q_t) { memcpy(hyp_q_t, o.pose.q, 32); memcpy(hyp_q_t + 4, o.pose.t, 24); }
     if (touched_nodes) *touched_nodes = o.touched;

@@ -677,7 +677,9 @@ __global__ void kdbg_five_point(const double *x1, const double *x2, uint32_t n, 
     if (i >= n) return;
     double a[10], b[10];
     for (int k = 0; k < 10; k++) { a[k] = x1[10 * (size_t)i + k]; b[k] = x2[10 * (size_t)i + k]; }
-    count[i] = fivePoint(a, b, Eout + 90 * (size_t)i, 10, dkMaxIters, dkTolSq);
+    // the legacy (tolerance 0) mode exercises the exact cycle jump used by K2
+    count[i] = dkTolSq == 0.0 ? fivePoint<true>(a, b, Eout + 90 * (size_t)i, 10, dkMaxIters, dkTolSq)
+                              : fivePoint<false>(a, b, Eout + 90 * (size_t)i, 10, dkMaxIters, dkTolSq);
 }
 }  // namespace
 

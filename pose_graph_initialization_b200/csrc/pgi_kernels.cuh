@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(64) k2_fivept_first_solution(WaveArgs a)
                 const double4 c = rows[selectRank(bits, nWords, i)];
                 x1[2 * i] = c.x; x1[2 * i + 1] = c.y; x2[2 * i] = c.z; x2[2 * i + 1] = c.w;
             }
-            found = fivePoint(x1, x2, E, 1, 1000, 0.0) > 0;
+            found = fivePoint<true>(x1, x2, E, 1, 1000, 0.0) > 0;
         } else {
             CvRng rng((uint64_t)-1);
             for (int iter = 0; iter < 1000 && !found; iter++) {
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(64) k2_fivept_first_solution(WaveArgs a)
                     const double4 c = rows[selectRank(bits, nWords, (uint32_t)idx_i)];
                     x1[2 * i] = c.x; x1[2 * i + 1] = c.y; x2[2 * i] = c.z; x2[2 * i + 1] = c.w;
                 }
-                found = fivePoint(x1, x2, E, 1, 1000, 0.0) > 0;
+                found = fivePoint<true>(x1, x2, E, 1, 1000, 0.0) > 0;
             }
         }
         if (!(flags & ST_NEED_5PT)) {
@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(64) k4_fallback_solve(WaveArgs a, int chunk)
         x1[2 * i] = c.x; x1[2 * i + 1] = c.y; x2[2 * i] = c.z; x2[2 * i + 1] = c.w;
     }
     double *out = a.fbSols + ((size_t)w * kFbChunk + j) * 90;
-    const int n = fivePoint(x1, x2, out, 10, kDkMaxSweeps, kDkTolSq);
+    const int n = fivePoint<false>(x1, x2, out, 10, kDkMaxSweeps, kDkTolSq);
     a.fbCounts[(size_t)w * kFbChunk + j] = (uint8_t)n;
 }
 

@@ -283,8 +283,51 @@ PGI_DEV Cx cdiv(Cx a, Cx b)
     return Cx{(a.re * b.re + a.im * b.im) * t, (-a.re * b.im + a.im * b.re) * t};
 }
 
-// cv::solvePoly (Durand-Kerner, Gauss-Seidel order), degree exactly NDEG (registers, fully unrolled).
+// One Gauss-Seidel Durand-Kerner sweep of cv::solvePoly on register-resident roots; returns max |correction|^2.
 template <int NDEG>
+__device__ __forceinline__ double dkSweep(const double (&co)[NDEG + 1], Cx (&roots)[NDEG])
+{
+    double maxDiffSq = 0;
+#pragma unroll
+    for (int i = 0; i < NDEG; i++) {
+        const Cx p = roots[i];
+        Cx num{co[NDEG], 0.0}, denom{co[NDEG], 0.0};
+#pragma unroll
+        for (int j = 0; j < NDEG; j++) {
+            num = cmul(num, p);
+            num.re = num.re + co[NDEG - j - 1];
+            num.im = num.im + 0.0;
+            if (j != i) {
+                const Cx d{p.re - roots[j].re, p.im - roots[j].im};
+                if (d.re != 0 || d.im != 0) denom = cmul(denom, d);
+            }
+        }
+        num = cdiv(num, denom);
+        roots[i].re = p.re - num.re;
+        roots[i].im = p.im - num.im;
+        const double m = num.re * num.re + num.im * num.im;
+        maxDiffSq = maxDiffSq < m ? m : maxDiffSq;
+    }
+    return maxDiffSq;
+}
+
+template <int NDEG>
+__device__ __forceinline__ bool sameRoots(const Cx (&a)[NDEG], const Cx (&b)[NDEG])
+{
+    bool same = true;
+#pragma unroll
+    for (int i = 0; i < NDEG; i++)
+        same &= (__double_as_longlong(a[i].re) == __double_as_longlong(b[i].re)) &&
+                (__double_as_longlong(a[i].im) == __double_as_longlong(b[i].im));
+    return same;
+}
+
+// cv::solvePoly (Durand-Kerner, Gauss-Seidel order), degree exactly NDEG (registers, fully unrolled).
+// cv::solvePoly always burns maxIters = 1000 sweeps (it only stops on a correction of exactly 0), but a sweep is a
+// deterministic map of the root vector, and in floating point that map falls into a short cycle (period 1-12
+// in > 97 % of cases) after ~30-50 sweeps.  CYCLE_JUMP detects the cycle exactly (Brent, bitwise state equality)
+// and jumps to the state sweep number maxIters would have produced: bit-identical to running every sweep.
+template <int NDEG, bool CYCLE_JUMP>
 __device__ __forceinline__ void dkSolveFixed(const double *c /*ascending, NDEG+1*/, Cx *rootsOut, int maxIters, double tolSq)
 {
     Cx roots[NDEG];
@@ -300,29 +343,36 @@ __device__ __forceinline__ void dkSolveFixed(const double *c /*ascending, NDEG+1
             p = cmul(p, r);
         }
     }
-    for (int iter = 0; iter < maxIters; iter++) {
-        double maxDiffSq = 0;
+    if (CYCLE_JUMP) {
+        Cx tort[NDEG];
 #pragma unroll
-        for (int i = 0; i < NDEG; i++) {
-            const Cx p = roots[i];
-            Cx num{co[NDEG], 0.0}, denom{co[NDEG], 0.0};
-#pragma unroll
-            for (int j = 0; j < NDEG; j++) {
-                num = cmul(num, p);
-                num.re = num.re + co[NDEG - j - 1];
-                num.im = num.im + 0.0;
-                if (j != i) {
-                    const Cx d{p.re - roots[j].re, p.im - roots[j].im};
-                    if (d.re != 0 || d.im != 0) denom = cmul(denom, d);
-                }
+        for (int i = 0; i < NDEG; i++) tort[i] = roots[i];
+        int power = 1, lam = 0, done = 0;  // `done` sweeps applied to `roots`; tort = state after (done - lam) sweeps
+        bool stopped = false;
+        while (done < maxIters) {
+            const double md = dkSweep<NDEG>(co, roots);
+            ++done; ++lam;
+            if (md <= tolSq) { stopped = true; break; }
+            if (sameRoots<NDEG>(roots, tort)) {
+                // state(done) == state(done - lam): period lam.  state(maxIters) == state(done + ((maxIters - done) % lam))
+                int rest = (maxIters - done) % lam;
+                for (; rest > 0; --rest) dkSweep<NDEG>(co, roots);  // no early stop possible inside a cycle whose sweeps all had md > tolSq
+                stopped = true;
+                break;
             }
-            num = cdiv(num, denom);
-            roots[i].re = p.re - num.re;
-            roots[i].im = p.im - num.im;
-            const double m = num.re * num.re + num.im * num.im;
-            maxDiffSq = maxDiffSq < m ? m : maxDiffSq;
+            if (power == lam) {
+#pragma unroll
+                for (int i = 0; i < NDEG; i++) tort[i] = roots[i];
+                power *= 2;
+                lam = 0;
+            }
         }
-        if (maxDiffSq <= tolSq) break;
+        (void)stopped;
+    } else {
+        for (int iter = 0; iter < maxIters; iter++) {
+            const double md = dkSweep<NDEG>(co, roots);
+            if (md <= tolSq) break;
+        }
     }
 #pragma unroll
     for (int i = 0; i < NDEG; i++) {
@@ -441,6 +491,7 @@ __device__ inline void pmulz(const double *a, int la, const double *b, int lb, d
 // EMEstimatorCallback::runKernel for exactly 5 points.  Writes up to maxOut (<=10) row-major unit-norm
 // essential matrices to Eout and returns the TOTAL number of solutions found (<= 10) when maxOut == 10,
 // or min(total, maxOut) when the caller only needs the first ones.
+template <bool CYCLE_JUMP>
 __device__ inline int fivePoint(const double x1[10], const double x2[10], double *Eout, int maxOut, int dkMaxIters,
                                 double dkTolSq)
 {
@@ -506,7 +557,7 @@ __device__ inline int fivePoint(const double x1[10], const double x2[10], double
     for (; n > 1; n--)
         if (fabs(c[n]) + 0.0 > DBL_EPSILON) break;
     if (n == 10)
-        dkSolveFixed<10>(c, roots, dkMaxIters, dkTolSq);
+        dkSolveFixed<10, CYCLE_JUMP>(c, roots, dkMaxIters, dkTolSq);
     else
         dkSolveGeneric(c, n, roots, dkMaxIters, dkTolSq);
 
