@@ -89,6 +89,14 @@ uint64_t pgb_remaining(pgb_builder *b);
 /* Install prefetched fallback verdicts (one per registered pair, index = pair id). */
 int32_t pgb_set_fallback_verdicts(pgb_builder *b, const pgi_verdict *verdicts, uint64_t n_pairs);
 
+/* Same for a subset: verdicts[i] belongs to pair_ids[i] (the prefetch may arrive in chunks, in queue order). */
+int32_t pgb_set_fallback_verdicts_some(pgb_builder *b, const uint32_t *pair_ids, const pgi_verdict *verdicts, uint64_t n);
+
+/* The static similarity-ordered queue: number of queued pairs / their registered pair ids in pop order
+ * (UINT32_MAX for a queued pair without correspondences). */
+uint64_t pgb_queue_size(pgb_builder *b);
+void pgb_queue_pairs(pgb_builder *b, uint32_t *pair_ids_out);
+
 /* Pop up to max_items pairs in queue order, run the speculative A* and emit them. Returns the item count. */
 uint32_t pgb_next_wave(pgb_builder *b, uint32_t max_items, pgb_item *items);
 

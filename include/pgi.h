@@ -116,6 +116,12 @@ pgi_status pgi_register_scene(pgi_ctx *ctx, uint64_t n_views, const double *foca
                               const uint32_t *pair_views, const uint64_t *m_offset, const uint32_t *matches,
                               double thr_px);
 
+/* Make `ctx` use the pairs registered in `owner` (same device) without copying them: a second context — its
+ * own stream, wave buffers and statistics — can then verify waves concurrently with the first (used to overlap
+ * the hypothesis-independent fallback with the sequential graph commit).  `owner` must outlive `ctx`'s use and
+ * must not re-register while shared. */
+pgi_status pgi_share_pairs(pgi_ctx *ctx, pgi_ctx *owner);
+
 /* Copy the device-built normalised correspondences / thresholds of one pair back (testing a1). */
 pgi_status pgi_read_pair(pgi_ctx *ctx, uint32_t pair_id, double *corr_xy4, uint64_t capacity_rows, uint64_t *n_rows,
                          double *thr_norm);

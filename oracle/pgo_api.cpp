@@ -120,7 +120,7 @@ void pgo_iters_table(int N, uint16_t *out)
     fb::itersTable(N, t);
     std::memcpy(out, t.data(), t.size() * sizeof(uint16_t));
 }
-void pgo_score_model(const double *corr, int N, const double *E, double thr, double *cost, int *inliers)
+void pgo_score_model(const double *corr, int N, const double *E, double thr, uint64_t *cost, int *inliers)
 {
     fb::scoreModel(corr, N, E, thr * thr, (1.5 * thr) * (1.5 * thr), *cost, *inliers);
 }

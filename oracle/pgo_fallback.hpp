@@ -14,8 +14,10 @@
 // sigma-consensus (BASELINE.json north_star: "hypothesis scoring, and least-squares LO refits").
 // PARITY UNPINNED w.r.t. cv2 for this stage: agreement with cv2.findEssentialMat(USAC_MAGSAC) is
 // statistical only and is reported by tests/test_fallback_vs_cv2.py, never assumed.  The CUDA fallback
-// kernels must match THIS restatement bit-for-bit, so every floating-point reduction below has a
-// fixed, documented order (kStride strided partial sums + fixed tree).
+// kernels must match THIS restatement bit-for-bit.  To make that independent of any summation order, every
+// reduction over correspondences is done in exact 64-bit FIXED POINT: each FP64 term is computed with IEEE
+// operations, converted to an integer once, and the integers are summed (associative, so the CUDA kernels are
+// free to reduce in any order / with atomics).
 #pragma once
 #include <algorithm>
 #include <cfloat>
@@ -33,25 +35,12 @@ namespace fb {
 
 constexpr int kMaxIters = 1000;       // cv::findEssentialMat default maxIters for the USAC overload
 constexpr double kConfidence = 0.99;  // pose_graph_builder.h:1042
-constexpr int kStride = 256;          // reduction lanes (== CTA width of the CUDA kernel)
 constexpr int kLoRounds = 4;          // max least-squares refits after each new best model
 constexpr int kLoMinInliers = 9;      // need > 8 points for the linear fit
 constexpr int kDkMaxSweeps = 200;     // Durand-Kerner sweeps for the fallback's minimal solver
 constexpr double kDkTolSq = 1e-26;    // stop when max |correction|^2 <= this
-
-// Fixed-order sum of kStride partials: intra-warp (32-wide) shuffle-down tree, then the 8 warp sums
-// by a stride-4/2/1 tree.  Mirrors __shfl_down_sync reduction in the CUDA kernel.
-inline double treeReduce(double *p)
-{
-    for (int w = 0; w < kStride / 32; w++)
-        for (int s = 16; s >= 1; s >>= 1)
-            for (int l = 0; l < s; l++) p[w * 32 + l] += p[w * 32 + l + s];
-    double q[kStride / 32];
-    for (int w = 0; w < kStride / 32; w++) q[w] = p[w * 32];
-    for (int s = kStride / 64; s >= 1; s >>= 1)
-        for (int w = 0; w < s; w++) q[w] += q[w + s];
-    return q[0];
-}
+constexpr double kCostOne = 4294967296.0;       // MSAC term of an outlier in fixed point (2^32)
+constexpr double kLsScale = 1099511627776.0;    // 2^40: fixed-point scale of the normal-equation products
 
 // Sampler table: iteration -> 5 indices.  Depends on N only.
 inline void samplerTable(int N, int iters, std::vector<uint32_t> &out)
@@ -92,21 +81,20 @@ inline void itersTable(int N, std::vector<uint16_t> &out)
     }
 }
 
-// MSAC cost with truncation T = (1.5 thr)^2 and inlier count at thr^2, strided partial sums.
-inline void scoreModel(const double *corr, int N, const double E[9], double thrSq, double truncSq, double &cost,
+// MSAC cost with truncation T = (1.5 thr)^2 and inlier count at thr^2.  Fixed point: an outlier (or NaN residual)
+// costs 2^32, an inlier (uint64)(r^2 * (1/T) * 2^32).
+inline void scoreModel(const double *corr, int N, const double E[9], double thrSq, double truncSq, uint64_t &cost,
                        int &inliers)
 {
-    double part[kStride];
-    for (int t = 0; t < kStride; t++) part[t] = 0.0;
+    const double invT = 1.0 / truncSq;
+    uint64_t acc = 0;
     int cnt = 0;
     for (int i = 0; i < N; i++) {
         const double r = sampsonSq(corr + 4 * i, E);
-        // NaN residuals (degenerate model) count as full-cost outliers
-        const double term = (r < truncSq) ? r : truncSq;
-        part[i % kStride] += term;
+        acc += (r < truncSq) ? (uint64_t)(r * invT * kCostOne) : (uint64_t)kCostOne;
         cnt += (r < thrSq) ? 1 : 0;
     }
-    cost = treeReduce(part);
+    cost = acc;
     inliers = cnt;
 }
 
@@ -160,9 +148,9 @@ inline void smallestEigvec9(double A[81], double v[9])
 // (U diag(1,1,0) V^T with the Eigen-style 3x3 JacobiSVD), unit Frobenius norm.
 inline bool lsRefit(const double *corr, int N, const double Ecur[9], double thrSq, double Eout[9])
 {
-    // 45 upper-triangular sums, each as kStride strided partials + tree
-    static thread_local std::vector<double> parts;
-    parts.assign((size_t)45 * kStride, 0.0);
+    // 45 upper-triangular sums in 2^-40 fixed point (order-free)
+    int64_t acc[45];
+    for (int e = 0; e < 45; e++) acc[e] = 0;
     int cnt = 0;
     for (int i = 0; i < N; i++) {
         const double *c = corr + 4 * i;
@@ -171,16 +159,16 @@ inline bool lsRefit(const double *corr, int N, const double Ecur[9], double thrS
         const double a[9] = {c[2] * c[0], c[2] * c[1], c[2], c[3] * c[0], c[3] * c[1], c[3], c[0], c[1], 1.0};
         int e = 0;
         for (int r = 0; r < 9; r++)
-            for (int s = r; s < 9; s++, e++) parts[(size_t)e * kStride + (i % kStride)] += a[r] * a[s];
+            for (int q = r; q < 9; q++, e++) acc[e] += (int64_t)std::llrint(a[r] * a[q] * kLsScale);
     }
     if (cnt < kLoMinInliers) return false;
     double M[81];
     int e = 0;
     for (int r = 0; r < 9; r++)
-        for (int s = r; s < 9; s++, e++) {
-            const double v = treeReduce(&parts[(size_t)e * kStride]);
-            M[r * 9 + s] = v;
-            M[s * 9 + r] = v;
+        for (int q = r; q < 9; q++, e++) {
+            const double v = (double)acc[e] / kLsScale;
+            M[r * 9 + q] = v;
+            M[q * 9 + r] = v;
         }
     double ev[9];
     smallestEigvec9(M, ev);
@@ -209,7 +197,7 @@ struct FallbackResult {
     int iterations = 0;  // iterations executed
     int models = 0;      // minimal models scored
     int loRuns = 0;      // LO refits scored
-    double cost = DBL_MAX;
+    uint64_t cost = UINT64_MAX;
 };
 
 // Five-point minimal solver for the fallback: same algebra as cvx::fivePointKernel but with a
@@ -235,7 +223,7 @@ inline FallbackResult runFallback(const double *corr, int N, double thr, uint8_t
     itersTable(N, iters);
 
     int maxIters = kMaxIters;
-    double bestCost = DBL_MAX;
+    uint64_t bestCost = UINT64_MAX;
     int bestInl = 0;
     double bestE[9] = {0};
     bool have = false;
@@ -250,7 +238,7 @@ inline FallbackResult runFallback(const double *corr, int N, double thr, uint8_t
         const int ns = fivePointFallback(x1, x2, sols);
         bool updated = false;
         for (int s = 0; s < ns; s++) {
-            double cost;
+            uint64_t cost;
             int inl;
             scoreModel(corr, N, sols + 9 * s, thrSq, truncSq, cost, inl);
             res.models++;
@@ -266,7 +254,7 @@ inline FallbackResult runFallback(const double *corr, int N, double thr, uint8_t
             for (int r = 0; r < kLoRounds; r++) {
                 double Els[9];
                 if (!lsRefit(corr, N, bestE, thrSq, Els)) break;
-                double cost;
+                uint64_t cost;
                 int inl;
                 scoreModel(corr, N, Els, thrSq, truncSq, cost, inl);
                 res.loRuns++;

@@ -237,7 +237,7 @@ def iters_table(N):
 
 def score_model(corr, E, thr):
     corr, E = _d(corr), _d(E).reshape(9)
-    cost, inl = C.c_double(0), C.c_int(0)
+    cost, inl = C.c_uint64(0), C.c_int(0)
     lib().pgo_score_model(_p(corr, _dp), C.c_int(len(corr)), _p(E, _dp), C.c_double(thr), C.byref(cost), C.byref(inl))
     return cost.value, inl.value
 

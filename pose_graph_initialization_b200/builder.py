@@ -12,6 +12,7 @@ NVLink on device buffers, gloo on CPU tensors in the tests) so that every rank r
 commit.  With world_size == 1 no collective is issued.
 """
 import ctypes as C
+import threading
 import time
 
 import numpy as np
@@ -49,7 +50,8 @@ class PgbCounters(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
-PGB_EXPORTS = ["pgb_create", "pgb_destroy", "pgb_remaining", "pgb_set_fallback_verdicts", "pgb_next_wave",
+PGB_EXPORTS = ["pgb_create", "pgb_destroy", "pgb_remaining", "pgb_set_fallback_verdicts", "pgb_set_fallback_verdicts_some",
+               "pgb_queue_size", "pgb_queue_pairs", "pgb_next_wave",
                "pgb_commit_wave", "pgb_edge_count", "pgb_copy_edges", "pgb_log_count", "pgb_copy_log", "pgb_get_counters",
                "pgb_astar"]
 
@@ -61,6 +63,7 @@ def _host_lib():
             getattr(lib, name)
         lib.pgb_create.restype = C.c_int32
         lib.pgb_remaining.restype = C.c_uint64
+        lib.pgb_queue_size.restype = C.c_uint64
         lib.pgb_edge_count.restype = C.c_uint64
         lib.pgb_log_count.restype = C.c_uint64
         lib.pgb_next_wave.restype = C.c_uint32
@@ -113,6 +116,19 @@ class HostBuilder:
         verdicts = np.ascontiguousarray(verdicts, dtype=VERDICT_DTYPE)
         if self.lib.pgb_set_fallback_verdicts(self.h, _ptr(verdicts), C.c_uint64(len(verdicts))) != 0:
             raise RuntimeError("pgb_set_fallback_verdicts failed")
+
+    def set_fallback_verdicts_some(self, pair_ids, verdicts):
+        pair_ids = np.ascontiguousarray(pair_ids, dtype=np.uint32)
+        verdicts = np.ascontiguousarray(verdicts, dtype=VERDICT_DTYPE)
+        if self.lib.pgb_set_fallback_verdicts_some(self.h, _ptr(pair_ids), _ptr(verdicts), C.c_uint64(len(pair_ids))) != 0:
+            raise RuntimeError("pgb_set_fallback_verdicts_some failed")
+
+    def queue_pairs(self):
+        n = int(self.lib.pgb_queue_size(self.h))
+        out = np.zeros(n, dtype=np.uint32)
+        if n:
+            self.lib.pgb_queue_pairs(self.h, _ptr(out))
+        return out
 
     def next_wave(self, max_items):
         items = np.zeros(max_items, dtype=ITEM_DTYPE)
@@ -218,7 +234,8 @@ class PoseGraphBuilder:
                  kTraversalHeuristicsWeight_=0.8, kSimilarityThreshold_=0.5, kInlierOutlierThreshold_=0.4,
                  kImagePath_="", kWorkspacePath_="", kSimilarityGraphPath_="", kFocalLengthPath_="",
                  kUsePathFinding_=True, kUseGPU_=True, kUseEpipolarHashing_=False, *, scene=None, device=0,
-                 wave_size=1024, prefetch_fallback=True, fallback_wave=2048, group=None, rank=0, world_size=1):
+                 wave_size=1024, prefetch_fallback=True, fallback_wave=2048, overlap_fallback=True, group=None, rank=0,
+                 world_size=1):
         if not kUseGPU_:
             raise ValueError("the B200 path has no CPU implementation (kUseGPU_ must be true)")
         if kUseEpipolarHashing_:
@@ -237,7 +254,11 @@ class PoseGraphBuilder:
         self.prefetch_fallback = prefetch_fallback
         self.fallback_wave = fallback_wave
         self.group, self.rank, self.world = group, rank, world_size
+        # overlap the hypothesis-independent fallback (second context, own stream) with the sequential waves;
+        # single-rank only: with several ranks the prefetch is sharded and all-gathered up front instead
+        self.overlap = bool(overlap_fallback and prefetch_fallback and world_size == 1)
         self.engine = None
+        self.engine_fb = None
         self.timing = {}
 
     # -- engine + registration (H2D inside, counted by the engine's stats) -----------------------------------
@@ -250,6 +271,28 @@ class PoseGraphBuilder:
             self.engine = _engine.Engine(device=self.device, min_inliers=self.min_inliers)
         sub = self.scene if self.world == 1 else shard_scene(self.scene, lo, hi)
         self.engine.register_scene(sub, self.thr_px)
+        if self.overlap:
+            if self.engine_fb is None:
+                self.engine_fb = _engine.Engine(device=self.device, min_inliers=self.min_inliers)
+            self.engine_fb.share_pairs(self.engine)
+
+    def engine_stats(self):
+        st = self.engine.stats()
+        if self.engine_fb is not None:
+            for k, v in self.engine_fb.stats().items():
+                st[k] += v
+        return st
+
+    def reset_engine_stats(self):
+        self.engine.reset_stats()
+        if self.engine_fb is not None:
+            self.engine_fb.reset_stats()
+
+    def close(self):
+        for e in (self.engine_fb, self.engine):
+            if e is not None:
+                e.close()
+        self.engine = self.engine_fb = None
 
     def _exchange(self, local, counts):
         if self.world == 1:
@@ -283,12 +326,49 @@ class PoseGraphBuilder:
         t_reg = time.perf_counter()
         host = HostBuilder(self.scene, lazy_fallback=not self.prefetch_fallback, **self.cfg)
         self.host = host
-        if self.prefetch_fallback:
+        lock = threading.Lock()
+        progress = threading.Condition(lock)
+        state = {"done_pos": 0, "error": None}
+        worker = None
+        Q = 0
+        if self.prefetch_fallback and self.overlap:
+            queue = host.queue_pairs()
+            Q = len(queue)
+
+            def prefetch_worker():
+                try:
+                    for s in range(0, Q, self.fallback_wave):
+                        ids = queue[s:s + self.fallback_wave]
+                        ids = ids[ids != np.uint32(0xFFFFFFFF)]
+                        v = self.engine_fb.run_wave(ids, None, None, flags=WAVE_FALLBACK) if len(ids) else np.zeros(0, dtype=VERDICT_DTYPE)
+                        with progress:
+                            host.set_fallback_verdicts_some(ids, v)
+                            state["done_pos"] = min(Q, s + self.fallback_wave)
+                            progress.notify_all()
+                except Exception as exc:  # surface engine failures in the main thread
+                    with progress:
+                        state["error"] = exc
+                        state["done_pos"] = Q
+                        progress.notify_all()
+
+            worker = threading.Thread(target=prefetch_worker, daemon=True)
+            worker.start()
+        elif self.prefetch_fallback:
             self._prefetch(host)
         t_pre = time.perf_counter()
         flags = WAVE_PATH if self.prefetch_fallback else (WAVE_PATH | WAVE_FALLBACK)
-        while host.remaining() > 0:
-            items = host.next_wave(self.wave_size)
+        while True:
+            with progress:
+                remaining = host.remaining()
+                if remaining == 0:
+                    break
+                if worker is not None:
+                    need = min(Q, (Q - remaining) + self.wave_size)
+                    while state["done_pos"] < need:
+                        progress.wait()
+                    if state["error"] is not None:
+                        raise state["error"]
+                items = host.next_wave(self.wave_size)
             todo = np.nonzero(items["need_gpu"])[0]
             verdicts = np.zeros(len(todo), dtype=VERDICT_DTYPE)
             if len(todo):
@@ -307,7 +387,10 @@ class PoseGraphBuilder:
                 parts = self._exchange(local, counts)
                 for r in range(self.world):
                     verdicts[np.nonzero(own == r)[0]] = parts[r]
-            host.commit_wave(verdicts)  # 0 while the wave still iterates towards its fixed point
+            with progress:
+                host.commit_wave(verdicts)  # 0 while the wave still iterates towards its fixed point
+        if worker is not None:
+            worker.join()
         t_end = time.perf_counter()
         self.timing = dict(register_s=t_reg - t0, prefetch_s=t_pre - t_reg, waves_s=t_end - t_pre, total_s=t_end - t0)
         edges = host.edges()

@@ -181,12 +181,17 @@ struct AStarOut {
     std::vector<uint32_t> expanded;  // vertices whose edge lists were read
 };
 
+// Heap entries describe a child lazily: (parent node, entry of the parent's edge list).  The child's vertex and
+// cost tuple are re-derived from the parent when (and only when) it is popped — the same IEEE operations on the
+// same operands — so only the ~1 % of pushed nodes that are ever popped get an arena record.
 struct HeapItem {
     double f;
-    uint32_t node;
+    uint32_t parent;  // arena index of the expanded node that pushed this child (UINT32_MAX: the start node)
+    uint32_t entry;   // index into the concatenated (committed ++ overlay) edge list the parent iterated
 };
 struct ArenaNode {
     uint32_t vertex, parent, depth;
+    uint32_t listOwner;  // vertex whose edge list this node iterated when it was expanded
     double c0, c1;
 };
 
@@ -259,26 +264,49 @@ void aStar(const GraphView &gv, const double *sim /*transposed*/, uint32_t V, ui
     S.heap.clear();
     S.arena.clear();
     auto cmp = [](const HeapItem &a, const HeapItem &b) { return a.f < b.f; };  // graph_traversal.h:669-673
-    S.arena.push_back(ArenaNode{from, UINT32_MAX, 0, 1.0, 0.0});  // cost (1,0,0)  :721
-    S.heap.push_back(HeapItem{0.0, 0});
-    std::push_heap(S.heap.begin(), S.heap.end(), cmp);
+    S.heap.push_back(HeapItem{0.0, UINT32_MAX, 0});  // start node, cost (1,0,0)  :721
     const double oneMinusWeight = 1.0 - weight;
     // `edges` keeps its previous content when a vertex has no list (pose_graph.h:145-146).  Every vertex reached by
     // the search has at least the edge it was reached through, and the source has edges whenever hasLink holds, so
     // the stale case cannot occur; the owner is tracked only to keep the restatement literal.
     uint32_t listOwner = UINT32_MAX;
     const double *simTo = sim + (size_t)to * V;  // transposed table: simTo[next] = similarity(next, to)
+    const uint32_t *mark = S.mark.data();
+    const uint32_t epoch = S.epoch;
+    // edge-list entry `idx` of vertex lv as seen by this search: committed entries first, then overlay entries
+    auto entryAt = [&](uint32_t lv, uint32_t idx) -> const Adj & {
+        const std::vector<Adj> &real = g.byVertex[lv];
+        return idx < real.size() ? real[idx] : gv.ov->byVertex[lv][idx - real.size()].a;
+    };
     while (!S.heap.empty()) {
-        const uint32_t ni = S.heap.front().node;
+        const HeapItem top = S.heap.front();
         ++out.touched;  // :750
         std::pop_heap(S.heap.begin(), S.heap.end(), cmp);
         S.heap.pop_back();
-        const ArenaNode node = S.arena[ni];
+        // materialise the popped node
+        ArenaNode node;
+        if (top.parent == UINT32_MAX) {
+            node = ArenaNode{from, UINT32_MAX, 0, UINT32_MAX, 1.0, 0.0};
+        } else {
+            const ArenaNode &pn = S.arena[top.parent];
+            const Adj &e = entryAt(pn.listOwner, top.entry);
+            uint32_t next = e.next;
+            if (pn.listOwner != pn.vertex) next = e.next == pn.vertex ? pn.listOwner : e.next;
+            double h = simTo[next];
+            h = h < 0.0 ? 0.0 : (1.0 < h ? 1.0 : h);
+            node.vertex = next;
+            node.parent = top.parent;
+            node.depth = pn.depth + 1;
+            node.listOwner = UINT32_MAX;
+            node.c0 = pn.c0 > e.score ? e.score : pn.c0;
+            node.c1 = pn.c1 < h ? h : pn.c1;
+        }
         if (node.depth > maxDepth) continue;  // :755
         const uint32_t v = node.vertex;
         if (v == to) {  // :766
             S.path.clear();
-            for (uint32_t k = ni; k != UINT32_MAX; k = S.arena[k].parent) S.path.push_back(S.arena[k].vertex);
+            S.path.push_back(v);
+            for (uint32_t k = node.parent; k != UINT32_MAX; k = S.arena[k].parent) S.path.push_back(S.arena[k].vertex);
             std::reverse(S.path.begin(), S.path.end());
             SE3 pose = se3Identity();  // recoverPath :304
             bool ok = true;
@@ -297,29 +325,33 @@ void aStar(const GraphView &gv, const double *sim /*transposed*/, uint32_t V, ui
             }
             continue;
         }
-        S.mark[v] = S.epoch;  // nodeStates[v] = Open  :814
+        S.mark[v] = epoch;  // nodeStates[v] = Open  :814
         out.expanded.push_back(v);
         const std::vector<Adj> &real = g.byVertex[v];
         const std::vector<OvAdj> *ovl = gv.ov ? &gv.ov->byVertex[v] : nullptr;
         const bool hasOv = ovl && !ovl->empty() && (*ovl)[0].pos < gv.cutoff;
         if (!real.empty() || hasOv) listOwner = v;  // :817
+        node.listOwner = listOwner;
+        const uint32_t ni = (uint32_t)S.arena.size();
+        S.arena.push_back(node);
         if (node.depth < maxDepth && listOwner != UINT32_MAX) {  // :820
             const uint32_t lv = listOwner;
+            const double c0 = node.c0, c1 = node.c1;
+            uint32_t idx = 0;
             auto visit = [&](const Adj &e) {
+                const uint32_t entry = idx++;
                 if (e.score < 0.0) return;  // kMinimumInlierRatio is `const bool` receiving 0.0 (:613, :839)
                 uint32_t next = e.next;     // (v == dst) ? src : dst  :838-840
                 if (lv != v) next = e.next == v ? lv : e.next;  // stale list of another vertex (unreachable, see above)
-                const double edgeCost = node.c0 > e.score ? e.score : node.c0;  // MIN :843
+                if (mark[next] == epoch) return;  // nodeStates.find(next) != end  :855-856
+                const double edgeCost = c0 > e.score ? e.score : c0;  // MIN :843
                 double h = simTo[next];  // getSimilarity(next, to)
                 h = h < 0.0 ? 0.0 : (1.0 < h ? 1.0 : h);  // std::clamp(similarity, 0, 1)  :594
-                const double nextToDest = node.c1 < h ? h : node.c1;  // MAX :847
+                const double nextToDest = c1 < h ? h : c1;  // MAX :847
                 const double combined = weight * edgeCost + oneMinusWeight * nextToDest;  // :851-852
-                if (S.mark[next] != S.epoch) {  // nodeStates.find(next) == end  :855-856
-                    S.arena.push_back(ArenaNode{next, ni, node.depth + 1, edgeCost, nextToDest});
-                    S.heap.push_back(HeapItem{combined, (uint32_t)S.arena.size() - 1});
-                    std::push_heap(S.heap.begin(), S.heap.end(), cmp);
-                    ++out.pushes;
-                }
+                S.heap.push_back(HeapItem{combined, ni, entry});
+                std::push_heap(S.heap.begin(), S.heap.end(), cmp);
+                ++out.pushes;
             };
             for (const Adj &e : g.byVertex[lv]) visit(e);
             if (gv.ov)
@@ -741,6 +773,26 @@ int32_t pgb_set_fallback_verdicts(pgb_builder *b, const pgi_verdict *verdicts, u
         b->fbHave[p] = 1;
     }
     return 0;
+}
+
+int32_t pgb_set_fallback_verdicts_some(pgb_builder *b, const uint32_t *pair_ids, const pgi_verdict *verdicts, uint64_t n)
+{
+    if (!b || !verdicts || !pair_ids) return -1;
+    for (uint64_t i = 0; i < n; i++) {
+        if (pair_ids[i] >= b->P) return -1;
+        b->fbCache[pair_ids[i]] = verdicts[i];
+        b->fbHave[pair_ids[i]] = 1;
+    }
+    return 0;
+}
+
+uint64_t pgb_queue_size(pgb_builder *b) { return b ? b->order.size() : 0; }
+void pgb_queue_pairs(pgb_builder *b, uint32_t *out)
+{
+    for (size_t i = 0; i < b->order.size(); i++) {
+        auto pi = b->pairIndex.find(edgeKey(b->order[i].first, b->order[i].second));
+        out[i] = pi == b->pairIndex.end() ? UINT32_MAX : pi->second;
+    }
 }
 
 static uint32_t emitItems(pgb_builder *b, pgb_item *items)

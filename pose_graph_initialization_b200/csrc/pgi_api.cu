@@ -29,10 +29,12 @@ struct Registration {
     uint64_t nPairs = 0, nRows = 0;
     uint32_t maxN = 0;
     std::vector<uint64_t> h_offset;
+    bool borrowed = false;  // device buffers belong to another context (pgi_share_pairs)
     size_t capRows = 0, capOffset = 0, capThr = 0, capPairTable = 0, capSampler = 0, capIters = 0, capTables = 0;
 };
 
 constexpr int kMaxChunks = 64;
+constexpr uint32_t kK5MaxSmemPts = 12288;  // 192 KB of float4
 
 }  // namespace
 
@@ -99,6 +101,7 @@ pgi_status growDevice(pgi_ctx *ctx, T **p, size_t &cap, size_t need)
 
 void freeReg(Registration &r)
 {
+    if (r.borrowed) { r = Registration(); return; }
     cudaFree(r.d_corr); cudaFree(r.d_offset); cudaFree(r.d_thr); cudaFree(r.d_pairTable);
     cudaFree(r.d_sampler); cudaFree(r.d_itersTab); cudaFree(r.d_itersOff);
     r = Registration();
@@ -322,12 +325,16 @@ pgi_status submitWave(pgi_ctx *ctx, const Registration &r, uint32_t n, const uin
         ctx->stats.launches += 1;
         if (flags & PGI_WAVE_FALLBACK) {
             const int chunks = (int)((ctx->cfg.fallback_max_iters + kFbChunk - 1) / kFbChunk);
+            // FP32 staging area of K5: the largest pair if it fits, else 0 (those pairs take the FP64-only path)
+            uint32_t smemPts = r.maxN <= kK5MaxSmemPts ? std::max<uint32_t>(r.maxN, 1) : kK5MaxSmemPts;
+            if ((size_t)smemPts * 16 > 48 * 1024)
+                CK(cudaFuncSetAttribute(k5_fallback_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)smemPts * 16)));
             ctx->nChunks = std::min(chunks, kMaxChunks);
             for (int c = 0; c < ctx->nChunks; c++) {
                 const uint32_t threads = n * kFbChunk;
                 k4_fallback_solve<<<(threads + 63) / 64, 64, 0, s>>>(a, c);
                 CK(cudaEventRecord(ctx->evChunk[c][0], s));
-                k5_fallback_score<<<n, kCtaThreads, 0, s>>>(a, c, c == ctx->nChunks - 1 ? 1 : 0);
+                k5_fallback_score<<<n, kCtaThreads, (size_t)smemPts * 16, s>>>(a, c, c == ctx->nChunks - 1 ? 1 : 0, smemPts);
                 CK(cudaEventRecord(ctx->evChunk[c][1], s));
                 ctx->stats.launches += 2;
             }
@@ -459,6 +466,7 @@ pgi_status pgi_register_pairs(pgi_ctx *ctx, uint64_t n_pairs, const uint64_t *co
     if (!ctx) return PGI_ERR_INVALID;
     if (ctx->inFlight) { ctx->err = "a wave is in flight"; return PGI_ERR_STATE; }
     CK(cudaSetDevice(ctx->cfg.device));
+    if (ctx->reg.borrowed) ctx->reg = Registration();
     return registerDense(ctx, ctx->reg, n_pairs, corr_offset, corr_xy4, thr_norm);
 }
 
@@ -474,6 +482,7 @@ pgi_status pgi_register_scene(pgi_ctx *ctx, uint64_t n_views, const double *foca
         return PGI_ERR_INVALID;
     }
     CK(cudaSetDevice(ctx->cfg.device));
+    if (ctx->reg.borrowed) ctx->reg = Registration();
     Registration &r = ctx->reg;
     const uint64_t nKp = kp_offset[n_views], nRows = m_offset[n_pairs];
     for (uint64_t p = 0; p < n_pairs; p++) {
@@ -530,6 +539,18 @@ pgi_status pgi_register_scene(pgi_ctx *ctx, uint64_t n_views, const double *foca
     cleanup();
 #undef CKC
     return buildTables(ctx, r);
+}
+
+pgi_status pgi_share_pairs(pgi_ctx *ctx, pgi_ctx *owner)
+{
+    if (!ctx || !owner || ctx == owner) return PGI_ERR_INVALID;
+    if (ctx->inFlight) { ctx->err = "a wave is in flight"; return PGI_ERR_STATE; }
+    if (ctx->cfg.device != owner->cfg.device) { ctx->err = "contexts are on different devices"; return PGI_ERR_INVALID; }
+    if (ctx->cfg.fallback_max_iters != owner->cfg.fallback_max_iters) { ctx->err = "fallback_max_iters differ"; return PGI_ERR_INVALID; }
+    freeReg(ctx->reg);
+    ctx->reg = owner->reg;  // shallow copy of the device pointers and host offsets
+    ctx->reg.borrowed = true;
+    return PGI_OK;
 }
 
 pgi_status pgi_read_pair(pgi_ctx *ctx, uint32_t pair_id, double *corr_xy4, uint64_t capacity_rows, uint64_t *n_rows,

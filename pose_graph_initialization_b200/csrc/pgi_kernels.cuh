@@ -18,7 +18,7 @@
 
 namespace pgi {
 
-constexpr int kCtaThreads = 256;      // == oracle fb::kStride (fixed reduction order)
+constexpr int kCtaThreads = 256;
 constexpr int kFbChunk = 125;         // fallback iterations solved per K4 launch
 constexpr int kLoRounds = 4;
 constexpr int kLoMinInliers = 9;
@@ -40,7 +40,7 @@ enum : uint32_t {
 // Per-wave-slot working state (device only).
 struct SlotState {
     double E[9];
-    double bestCost;
+    unsigned long long bestCost;  // fixed-point MSAC cost of the best model so far (~0ull: none)
     double bestE[9];
     uint32_t flags;
     uint32_t testCount;
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(64) k2_fivept_first_solution(WaveArgs a)
         const uint32_t N = (uint32_t)(a.offset[pid + 1] - a.offset[pid]);
         flags |= ST_NEED_FB | ST_FB_RAN;
         if (N >= 5) flags |= ST_FB_ACTIVE;
-        s.bestCost = DBL_MAX;
+        s.bestCost = ~0ull;
         s.bestInl = 0;
         s.maxIters = (int)a.fbMaxIters;
         s.it = 0;
@@ -335,29 +335,20 @@ __global__ void __launch_bounds__(64) k4_fallback_solve(WaveArgs a, int chunk)
     a.fbCounts[(size_t)w * kFbChunk + j] = (uint8_t)n;
 }
 
-// Fixed-order block reduction of one double per thread (256 threads): intra-warp shuffle-down tree,
-// then a stride-4/2/1 tree over the 8 warp sums — the order the oracle's fb::treeReduce restates.
-__device__ __forceinline__ double blockReduceFixed(double v, double *sWarp /*8*/)
+// ---------------------------------------------------------------------------------------------
+// K5 building blocks.  Every reduction over correspondences is an exact 64-bit fixed-point sum (see
+// oracle/pgo_fallback.hpp): terms are produced by IEEE FP64 operations, converted to integers once and
+// added with integer arithmetic, so warps/CTAs may reduce in any order (shuffles, shared-memory atomics).
+// ---------------------------------------------------------------------------------------------
+constexpr double kCostOne = 4294967296.0;     // fixed-point MSAC cost of an outlier (2^32)
+constexpr double kLsScale = 1099511627776.0;  // 2^40: fixed-point scale of the normal-equation products
+constexpr int kQueueCap = 64;                 // per-warp queue of correspondences awaiting the exact FP64 path
+
+__device__ __forceinline__ unsigned long long warpSumU64(unsigned long long v)
 {
 #pragma unroll
     for (int s = 16; s >= 1; s >>= 1) v += __shfl_down_sync(0xffffffffu, v, s);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __syncthreads();
-    if (lane == 0) sWarp[warp] = v;
-    __syncthreads();
-    double r = 0.0;
-    if (threadIdx.x == 0) {
-        double q[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) q[k] = sWarp[k];
-#pragma unroll
-        for (int s = 4; s >= 1; s >>= 1)
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                if (k < s) q[k] += q[k + s];
-        r = q[0];
-    }
-    return r;  // valid in thread 0
+    return v;  // valid in lane 0
 }
 
 __device__ __forceinline__ uint32_t blockSumU32(uint32_t v, uint32_t *sWarp /*8*/)
@@ -373,31 +364,100 @@ __device__ __forceinline__ uint32_t blockSumU32(uint32_t v, uint32_t *sWarp /*8*
     return r;  // valid in all threads
 }
 
-// MSAC cost (truncation (1.5 thr)^2) + inlier count at thr^2 of one model; thread t owns points
-// i = t, t+256, ... in ascending order.  Returns cost in thread 0, inlier count in all threads.
-__device__ __forceinline__ void scoreModelBlock(const double4 *rows, uint32_t N, const double E[9], double thrSq,
-                                                double truncSq, double *sWarpD, uint32_t *sWarpU, double &cost,
-                                                uint32_t &inl)
+// FP32 certificate constants (see scoreModelWarp).
+struct F32Consts {
+    float rOut;  // |r_f32| above this certifies "outside the truncation band" (see scoreModelWarp)
+};
+
+__device__ __forceinline__ void exactTerm(const double4 *rows, uint32_t i, const double *Eg, double thrSq, double truncSq,
+                                          double invT, unsigned long long &cost, uint32_t &inl)
 {
-    double part = 0.0;
-    uint32_t cnt = 0;
-    for (uint32_t i = threadIdx.x; i < N; i += kCtaThreads) {
-        const double4 c = rows[i];
-        const double r = sampsonSq(c.x, c.y, c.z, c.w, E);
-        part += (r < truncSq) ? r : truncSq;
-        cnt += (r < thrSq) ? 1u : 0u;
-    }
-    cost = blockReduceFixed(part, sWarpD);
-    inl = blockSumU32(cnt, sWarpU);
+    double Ed[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) Ed[k] = Eg[k];
+    const double4 c = rows[i];
+    const double rr = sampsonSq(c.x, c.y, c.z, c.w, Ed);
+    cost += (rr < truncSq) ? (unsigned long long)(rr * invT * kCostOne) : (unsigned long long)kCostOne;
+    inl += (rr < thrSq) ? 1u : 0u;
 }
 
-// Symmetric 9x9 cyclic Jacobi, eigenvector of the smallest eigenvalue (single thread; mirrors the oracle).
-__device__ inline void smallestEigvec9(double *A /*81*/, double *V /*81*/, double v[9])
+// Score one model over the pair: thread t handles the points t, t + 256, ...
+// FP32 (FMA, shared-memory float4 copy) only CERTIFIES that a correspondence is far outside the truncation band
+// — then its term is exactly 2^32 and it is no inlier.  With r = x2h^T E x1h the Sampson numerator and
+// denom = |(E^T x2h)_xy|^2 + |(E x1h)_xy|^2 <= ||E||_F^2 (|x1h|^2 + |x2h|^2) = D  (models have unit Frobenius norm):
+//     |r_f32 - r| <= 4.2e-7 B < eAbs := 1e-6 max_i B_i,  B = (|x1|+|y1|+1)(|x2|+|y2|+1)   (input + 8 FMA roundings)
+//  => |r_f32| > rOut := sqrt(truncSq max_i D_i)(1 + 2^-10) + eAbs   implies   r^2 / denom > truncSq.
+// One 8-FMA chain and one compare per (model, correspondence).  Everything not certified (inliers, near-band
+// points, NaNs) is queued per warp and evaluated DENSELY, 32 at a time, by the exact FP64 path, so the FP64 pipe
+// only sees the few percent of evaluations that can matter.  Returns the warp's partial (cost, inliers) in lane 0.
+template <bool USE_F32>
+__device__ __forceinline__ void scoreModelWarp(const double4 *rows, const float4 *pts, uint32_t N, const double *Eg /*9, global/shared*/,
+                                               double thrSq, double truncSq, double invT, F32Consts fc, uint32_t *queue /*kQueueCap*/,
+                                               unsigned long long &costOut, uint32_t &inlOut)
 {
-    for (int i = 0; i < 9; i++)
-        for (int j = 0; j < 9; j++) V[i * 9 + j] = i == j ? 1.0 : 0.0;
+    const int lane = threadIdx.x & 31;
+    unsigned long long cost = 0;
+    uint32_t inl = 0, nOut = 0;
+    const double *Ed = Eg;  // the exact path re-reads the model (L1/shared) instead of pinning 18 registers
+    if (USE_F32) {
+        float E[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) E[k] = (float)Eg[k];
+        uint32_t qn = 0;  // warp-uniform
+        const uint32_t nRound = (N + kCtaThreads - 1) / kCtaThreads * kCtaThreads;
+        for (uint32_t i = threadIdx.x; i < nRound; i += kCtaThreads) {
+            bool unsure = false;
+            if (i < N) {
+                const float4 p = pts[i];
+                const float rxc = fmaf(E[0], p.z, fmaf(E[3], p.w, E[6]));
+                const float ryc = fmaf(E[1], p.z, fmaf(E[4], p.w, E[7]));
+                const float rwc = fmaf(E[2], p.z, fmaf(E[5], p.w, E[8]));
+                const float r = fmaf(p.x, rxc, fmaf(p.y, ryc, rwc));
+                const bool outside = fabsf(r) > fc.rOut;  // false for NaN
+                nOut += outside ? 1u : 0u;
+                unsure = !outside;
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, unsure);
+            if (m) {
+                if (unsure) queue[qn + __popc(m & ((1u << lane) - 1u))] = i;
+                qn += __popc(m);
+                __syncwarp();
+                if (qn >= 32) {
+                    const uint32_t idx = queue[lane];
+                    exactTerm(rows, idx, Ed, thrSq, truncSq, invT, cost, inl);
+                    const uint32_t rest = qn - 32;  // < 32
+                    const uint32_t moved = lane < rest ? queue[32 + lane] : 0u;
+                    __syncwarp();
+                    if (lane < rest) queue[lane] = moved;
+                    qn = rest;
+                    __syncwarp();
+                }
+            }
+        }
+        if (qn) {
+            if ((uint32_t)lane < qn) exactTerm(rows, queue[lane], Ed, thrSq, truncSq, invT, cost, inl);
+            __syncwarp();
+        }
+    } else {
+        for (uint32_t i = threadIdx.x; i < N; i += kCtaThreads) exactTerm(rows, i, Ed, thrSq, truncSq, invT, cost, inl);
+    }
+    cost += (unsigned long long)nOut << 32;
+    costOut = warpSumU64(cost);
+    inlOut = __reduce_add_sync(0xffffffffu, inl);
+}
+
+// Symmetric 9x9 cyclic Jacobi, eigenvector of the smallest eigenvalue.  Same rotation sequence and the same
+// per-element operations as the oracle's sequential loops; the 9 independent element updates of each phase are
+// spread over lanes 0..8 of the calling warp (A, V in shared memory, __syncwarp between phases).  A one-thread
+// version of this solve (dependent shared-memory round trips) dominated K5 before.
+__device__ inline void smallestEigvec9Warp(double *A /*81 shared*/, double *V /*81 shared*/, double *vOut /*9 shared*/)
+{
+    const int k = threadIdx.x & 31;
+    if (k < 9)
+        for (int j = 0; j < 9; j++) V[k * 9 + j] = k == j ? 1.0 : 0.0;
+    __syncwarp();
     for (int sweep = 0; sweep < 30; sweep++) {
-        double off = 0.0, diag = 0.0;
+        double off = 0.0, diag = 0.0;  // every lane evaluates the same sums in the oracle's order
         for (int i = 0; i < 9; i++) {
             diag += A[i * 9 + i] * A[i * 9 + i];
             for (int j = i + 1; j < 9; j++) off += A[i * 9 + j] * A[i * 9 + j];
@@ -406,68 +466,88 @@ __device__ inline void smallestEigvec9(double *A /*81*/, double *V /*81*/, doubl
         for (int p = 0; p < 8; p++)
             for (int q = p + 1; q < 9; q++) {
                 const double apq = A[p * 9 + q];
-                if (apq == 0.0) continue;
+                if (apq == 0.0) continue;  // warp-uniform
                 const double app = A[p * 9 + p], aqq = A[q * 9 + q];
                 const double tau = (aqq - app) / (2.0 * apq);
                 const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
                 const double c = 1.0 / sqrt(1.0 + t * t), s = t * c;
-                for (int k = 0; k < 9; k++) {
+                __syncwarp();
+                if (k < 9) {  // columns p, q
                     const double akp = A[k * 9 + p], akq = A[k * 9 + q];
                     A[k * 9 + p] = c * akp - s * akq;
                     A[k * 9 + q] = s * akp + c * akq;
                 }
-                for (int k = 0; k < 9; k++) {
+                __syncwarp();
+                if (k < 9) {  // rows p, q, and the eigenvector accumulation
                     const double apk = A[p * 9 + k], aqk = A[q * 9 + k];
                     A[p * 9 + k] = c * apk - s * aqk;
                     A[q * 9 + k] = s * apk + c * aqk;
-                }
-                for (int k = 0; k < 9; k++) {
                     const double vkp = V[k * 9 + p], vkq = V[k * 9 + q];
                     V[k * 9 + p] = c * vkp - s * vkq;
                     V[k * 9 + q] = s * vkp + c * vkq;
                 }
+                __syncwarp();
             }
     }
     int m = 0;
     for (int i = 1; i < 9; i++)
         if (A[i * 9 + i] < A[m * 9 + m]) m = i;
-    for (int k = 0; k < 9; k++) v[k] = V[k * 9 + m];
+    if (k < 9) vOut[k] = V[k * 9 + m];
+    __syncwarp();
 }
 
-// Least-squares refit on the inliers of Ecur (8-point normal equations, essential projection).
-// Whole CTA cooperates; result valid in shared sEls / *ok (after the trailing __syncthreads).
-__device__ inline void lsRefitBlock(const double4 *rows, uint32_t N, const double Ecur[9], double thrSq, double *sM /*81*/,
-                                    double *sV /*81*/, double *sWarpD, uint32_t *sWarpU, double *sEls /*9*/, int *sOk)
+// Least-squares refit on the inliers of Ecur (8-point normal equations in 2^-40 fixed point, essential projection).
+// Whole CTA cooperates; result in shared sEls / *sOk (valid after the trailing __syncthreads).
+__device__ inline void lsRefitBlock(const double4 *rows, uint32_t N, const double Ecur[9], double thrSq, long long *sAcc /*45*/,
+                                    double *sM /*81*/, double *sV /*81*/, uint32_t *sWarpU, double *sEls /*9*/, int *sOk)
 {
-    // 9 passes: pass r accumulates the (9 - r) sums  sum a_r a_s, s >= r  (thread t: points t, t+256, ...)
+    if (threadIdx.x < 45) sAcc[threadIdx.x] = 0;
     uint32_t cntLocal = 0;
-    for (int r = 0; r < 9; r++) {
-        double acc[9];
+    __syncthreads();
+    // 3 sub-passes x 15 upper-triangular entries keep the accumulators in registers
+#pragma unroll 1
+    for (int sp = 0; sp < 3; sp++) {
+        long long acc[15];
 #pragma unroll
-        for (int s = 0; s < 9; s++) acc[s] = 0.0;
+        for (int e = 0; e < 15; e++) acc[e] = 0;
         for (uint32_t i = threadIdx.x; i < N; i += kCtaThreads) {
             const double4 c = rows[i];
             if (!(sampsonSq(c.x, c.y, c.z, c.w, Ecur) < thrSq)) continue;
-            if (r == 0) cntLocal++;
+            if (sp == 0) cntLocal++;
             const double av[9] = {c.z * c.x, c.z * c.y, c.z, c.w * c.x, c.w * c.y, c.w, c.x, c.y, 1.0};
-            double ar = av[0];
+            // entries e = 15 sp .. 15 sp + 14 of the row-major upper triangle (r <= q)
+            int e = 0;
 #pragma unroll
-            for (int s = 1; s < 9; s++) ar = (s == r) ? av[s] : ar;
+            for (int r = 0; r < 9; r++)
 #pragma unroll
-            for (int s = 0; s < 9; s++)
-                if (s >= r) acc[s] += ar * av[s];
+                for (int q = r; q < 9; q++, e++)
+                    if (e / 15 == sp) acc[e % 15] += __double2ll_rn(av[r] * av[q] * kLsScale);
         }
-        for (int s = r; s < 9; s++) {
-            const double v = blockReduceFixed(acc[s], sWarpD);
-            if (threadIdx.x == 0) { sM[r * 9 + s] = v; sM[s * 9 + r] = v; }
+#pragma unroll
+        for (int e = 0; e < 15; e++) {
+            const unsigned long long v = warpSumU64((unsigned long long)acc[e]);
+            if ((threadIdx.x & 31) == 0) atomicAdd((unsigned long long *)&sAcc[sp * 15 + e], v);
         }
     }
-    const uint32_t cnt = blockSumU32(cntLocal, sWarpU);
+    const uint32_t cnt = blockSumU32(cntLocal, sWarpU);  // also orders the atomics before the reads below
+    if (threadIdx.x < 32 && cnt >= (uint32_t)kLoMinInliers) {  // warp 0
+        if (threadIdx.x == 0) {
+            int e = 0;
+            for (int r = 0; r < 9; r++)
+                for (int q = r; q < 9; q++, e++) {
+                    const double v = (double)sAcc[e] / kLsScale;
+                    sM[r * 9 + q] = v;
+                    sM[q * 9 + r] = v;
+                }
+        }
+        __syncwarp();
+        smallestEigvec9Warp(sM, sV, sEls);
+    }
     if (threadIdx.x == 0) {
         int ok = 0;
         if (cnt >= (uint32_t)kLoMinInliers) {
             double ev[9];
-            smallestEigvec9(sM, sV, ev);
+            for (int k = 0; k < 9; k++) ev[k] = sEls[k];
             double U[9], V[9], S[3];
             eigenJacobiSvd<3, true, true>(ev, U, V, S);
             if (S[1] > 0.0) {
@@ -493,17 +573,15 @@ __device__ inline void lsRefitBlock(const double4 *rows, uint32_t N, const doubl
 }
 
 // ---------------------------------------------------------------------------------------------
-// K5: one CTA per wave pair; walks the chunk's iterations IN ORDER (best-so-far / LO / termination
-// semantics of a sequential RANSAC), scoring every minimal model over all N correspondences.
-// Correspondences are streamed from L2/HBM (32 B / row / model).
+// K5: one CTA per wave pair; walks the chunk's iterations IN ORDER (best-so-far / LO / termination semantics of a
+// sequential RANSAC).  All models of an iteration are scored by the whole CTA (FP32-certified, exact FP64 where it
+// matters), their fixed-point costs land in shared memory through atomics, one barrier, then thread 0 decides.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kCtaThreads) k5_fallback_score(WaveArgs a, int chunk, int lastChunk)
+template <bool USE_F32>
+__device__ __forceinline__ void k5Body(const WaveArgs &a, int chunk, int lastChunk, uint32_t w, float4 *sPts)
 {
-    const uint32_t w = blockIdx.x;
-    if (w >= a.n) return;
     SlotState &st = a.state[w];
     const uint32_t flags0 = st.flags;
-    if (!(flags0 & ST_NEED_FB)) return;
     const uint32_t pid = a.pairId[w];
     const uint64_t r0 = a.offset[pid];
     const uint32_t N = (uint32_t)(a.offset[pid + 1] - r0);
@@ -512,70 +590,120 @@ __global__ void __launch_bounds__(kCtaThreads) k5_fallback_score(WaveArgs a, int
     const double thrSq = thr * thr;
     const double trunc = 1.5 * thr;
     const double truncSq = trunc * trunc;
+    const double invT = 1.0 / truncSq;
 
-    __shared__ double sWarpD[8];
     __shared__ uint32_t sWarpU[8];
+    __shared__ uint32_t sQueue[kCtaThreads / 32][kQueueCap];
+    __shared__ unsigned long long sCost[2][10];
+    __shared__ uint32_t sInl[2][10];
+    __shared__ float sMaxB[8], sMaxD[8];
+    __shared__ long long sAcc[45];
     __shared__ double sM[81], sV[81], sEls[9], sBestE[9];
-    __shared__ double sBestCost;
+    __shared__ unsigned long long sBestCost;
     __shared__ int sBestInl, sMaxIters, sOk, sUpdated, sHave;
 
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         sBestCost = st.bestCost;
         sBestInl = st.bestInl;
         sMaxIters = st.maxIters;
-        sHave = st.bestCost < DBL_MAX ? 1 : 0;
+        sHave = st.bestCost != ~0ull ? 1 : 0;
         for (int k = 0; k < 9; k++) sBestE[k] = st.bestE[k];
     }
+    if (threadIdx.x < 20) { sCost[threadIdx.x / 10][threadIdx.x % 10] = 0; sInl[threadIdx.x / 10][threadIdx.x % 10] = 0; }
+    const bool active = (flags0 & ST_FB_ACTIVE) != 0;
+    F32Consts fc{3.0e38f};
+    if (USE_F32 && active) {
+        float maxB = 0.f, maxD = 0.f;
+        for (uint32_t i = threadIdx.x; i < N; i += kCtaThreads) {
+            const double4 c = rows[i];
+            const float4 p = make_float4((float)c.x, (float)c.y, (float)c.z, (float)c.w);
+            sPts[i] = p;
+            const float B = (fabsf(p.x) + fabsf(p.y) + 1.0f) * (fabsf(p.z) + fabsf(p.w) + 1.0f);
+            const float D = (p.x * p.x + p.y * p.y + 1.0f) + (p.z * p.z + p.w * p.w + 1.0f);
+            maxB = fmaxf(maxB, B == B ? B : 3.0e38f);  // NaN coordinates: make the certificate unreachable
+            maxD = fmaxf(maxD, D == D ? D : 3.0e38f);
+        }
+#pragma unroll
+        for (int sh = 16; sh >= 1; sh >>= 1) {
+            maxB = fmaxf(maxB, __shfl_xor_sync(0xffffffffu, maxB, sh));
+            maxD = fmaxf(maxD, __shfl_xor_sync(0xffffffffu, maxD, sh));
+        }
+        if (lane == 0) { sMaxB[warp] = maxB; sMaxD[warp] = maxD; }
+    }
     __syncthreads();
+    if (USE_F32 && active) {
+        float maxB = 0.f, maxD = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { maxB = fmaxf(maxB, sMaxB[k]); maxD = fmaxf(maxD, sMaxD[k]); }
+        // computed in FP64 and rounded up: sqrt(truncSq * Dmax (1 + 2^-20)) (1 + 2^-10) + 1e-6 Bmax
+        const double rOut = sqrt(truncSq * ((double)maxD * (1.0 + 9.5367431640625e-7))) * (1.0 + 9.765625e-4) + 1e-6 * (double)maxB;
+        fc.rOut = (rOut < 1e30 && rOut == rOut) ? (float)(rOut * (1.0 + 1.1920928955078125e-7)) : 3.0e38f;
+    }
     uint32_t models = 0;
+    int parity = 0;
     int it = st.it;
-    if (flags0 & ST_FB_ACTIVE) {
+    if (active) {
         const uint16_t *itTab = a.itersTab + a.itersTabOff[st.tableIdx];
         const int itEnd = (chunk + 1) * kFbChunk;
         for (; it < itEnd && it < sMaxIters; ++it) {
             const int j = it - chunk * kFbChunk;
             const int ns = a.fbCounts[(size_t)w * kFbChunk + j];
             const double *sols = a.fbSols + ((size_t)w * kFbChunk + j) * 90;
-            if (threadIdx.x == 0) sUpdated = 0;
-            for (int s = 0; s < ns; s++) {
-                double E[9];
-#pragma unroll
-                for (int k = 0; k < 9; k++) E[k] = sols[s * 9 + k];
-                double cost;
-                uint32_t inl;
-                scoreModelBlock(rows, N, E, thrSq, truncSq, sWarpD, sWarpU, cost, inl);
-                models++;
-                if (threadIdx.x == 0 && cost < sBestCost) {
-                    sBestCost = cost;
-                    sBestInl = (int)inl;
-                    for (int k = 0; k < 9; k++) sBestE[k] = E[k];
-                    sUpdated = 1;
-                    sHave = 1;
+            for (int q = 0; q < ns; q++) {
+                unsigned long long c;
+                uint32_t n;
+                scoreModelWarp<USE_F32>(rows, sPts, N, sols + q * 9, thrSq, truncSq, invT, fc, sQueue[warp], c, n);
+                if (lane == 0) {
+                    atomicAdd(&sCost[parity][q], c);
+                    atomicAdd(&sInl[parity][q], n);
                 }
             }
+            models += ns;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int upd = 0;
+                for (int q = 0; q < ns; q++) {
+                    if (sCost[parity][q] < sBestCost) {
+                        sBestCost = sCost[parity][q];
+                        sBestInl = (int)sInl[parity][q];
+                        for (int k = 0; k < 9; k++) sBestE[k] = sols[q * 9 + k];
+                        upd = 1;
+                        sHave = 1;
+                    }
+                    sCost[parity][q] = 0;  // ready for the iteration after next (a barrier away)
+                    sInl[parity][q] = 0;
+                }
+                sUpdated = upd;
+            }
+            parity ^= 1;
             __syncthreads();
             if (sUpdated) {
                 for (int r = 0; r < kLoRounds; r++) {
                     double Eb[9];
 #pragma unroll
                     for (int k = 0; k < 9; k++) Eb[k] = sBestE[k];
-                    lsRefitBlock(rows, N, Eb, thrSq, sM, sV, sWarpD, sWarpU, sEls, &sOk);
+                    lsRefitBlock(rows, N, Eb, thrSq, sAcc, sM, sV, sWarpU, sEls, &sOk);
                     if (!sOk) break;
-                    double El[9];
-#pragma unroll
-                    for (int k = 0; k < 9; k++) El[k] = sEls[k];
-                    double cost;
-                    uint32_t inl;
-                    scoreModelBlock(rows, N, El, thrSq, truncSq, sWarpD, sWarpU, cost, inl);
+                    unsigned long long c;
+                    uint32_t n;
+                    scoreModelWarp<USE_F32>(rows, sPts, N, sEls, thrSq, truncSq, invT, fc, sQueue[warp], c, n);
+                    if (lane == 0) {
+                        atomicAdd(&sCost[parity][0], c);
+                        atomicAdd(&sInl[parity][0], n);
+                    }
                     models++;
+                    __syncthreads();
                     if (threadIdx.x == 0) {
-                        if (cost < sBestCost) {
-                            sBestCost = cost;
-                            sBestInl = (int)inl;
-                            for (int k = 0; k < 9; k++) sBestE[k] = El[k];
+                        if (sCost[parity][0] < sBestCost) {
+                            sBestCost = sCost[parity][0];
+                            sBestInl = (int)sInl[parity][0];
+                            for (int k = 0; k < 9; k++) sBestE[k] = sEls[k];
                             sOk = 1;
                         } else
                             sOk = 0;
+                        sCost[parity][0] = 0;
+                        sInl[parity][0] = 0;
                     }
                     __syncthreads();
                     if (!sOk) break;
@@ -589,7 +717,7 @@ __global__ void __launch_bounds__(kCtaThreads) k5_fallback_score(WaveArgs a, int
         }
     }
     __syncthreads();
-    const bool done = !(flags0 & ST_FB_ACTIVE) || it >= sMaxIters || lastChunk;
+    const bool done = !active || it >= sMaxIters || lastChunk;
     // finalise: mask == sampson^2(E_final) < thr^2 and its count
     uint32_t finalInl = 0;
     if (done) {
@@ -629,6 +757,20 @@ __global__ void __launch_bounds__(kCtaThreads) k5_fallback_score(WaveArgs a, int
         }
         st.flags = f;
     }
+}
+
+__global__ void __launch_bounds__(kCtaThreads, 3) k5_fallback_score(WaveArgs a, int chunk, int lastChunk, uint32_t smemPts)
+{
+    extern __shared__ float4 sPts[];  // smemPts float4 slots (FP32 copy of the pair's correspondences)
+    const uint32_t w = blockIdx.x;
+    if (w >= a.n) return;
+    if (!(a.state[w].flags & ST_NEED_FB)) return;
+    const uint32_t pid = a.pairId[w];
+    const uint32_t N = (uint32_t)(a.offset[pid + 1] - a.offset[pid]);
+    if (N <= smemPts)
+        k5Body<true>(a, chunk, lastChunk, w, sPts);
+    else
+        k5Body<false>(a, chunk, lastChunk, w, sPts);  // pair too large to stage: exact FP64 for every point
 }
 
 // Whole-CTA E -> candidates -> triangulation vote (pose_utils.h:172-240).  Results in shared memory.

@@ -44,7 +44,7 @@ class PgiStats(C.Structure):
 
 EXPORTS = [
     "pgi_version", "pgi_device_count", "pgi_create", "pgi_destroy", "pgi_last_error", "pgi_register_pairs",
-    "pgi_register_scene", "pgi_read_pair", "pgi_submit_wave", "pgi_wait_wave", "pgi_wait_wave_device",
+    "pgi_register_scene", "pgi_share_pairs", "pgi_read_pair", "pgi_submit_wave", "pgi_wait_wave", "pgi_wait_wave_device",
     "pgi_estimate_pose", "pgi_test_pose", "pgi_get_stats", "pgi_reset_stats", "pgi_dbg_sampson",
     "pgi_dbg_five_point", "pgi_dbg_pose_from_essential", "pgi_dbg_fp64_peak",
 ]
@@ -73,6 +73,7 @@ def load_library():
         getattr(lib, name)  # AttributeError if a declared symbol is missing
     for name in EXPORTS[5:]:
         getattr(lib, name).restype = C.c_int32
+    lib.pgi_share_pairs.argtypes = [C.c_void_p, C.c_void_p]
     lib.pgi_destroy.argtypes = [C.c_void_p]
     _lib = lib
     return lib
@@ -142,6 +143,11 @@ class Engine:
         self._ck(self.lib.pgi_register_scene(self.h, C.c_uint64(len(focal)), _ptr(focal), _ptr(size), _ptr(kpo), _ptr(kp),
                                              C.c_uint64(len(pv)), _ptr(pv), _ptr(mo), _ptr(mt), C.c_double(thr_px)))
         self.n_pairs, self.offset = len(pv), mo.copy()
+
+    def share_pairs(self, owner):
+        """Use the pairs registered in `owner` (same device) without copying them."""
+        self._ck(self.lib.pgi_share_pairs(self.h, owner.h))
+        self.n_pairs, self.offset = owner.n_pairs, owner.offset
 
     def read_pair(self, pair_id):
         n = int(self.offset[pair_id + 1] - self.offset[pair_id])

@@ -2,6 +2,11 @@ set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 make -C oracle -s 2>&1 | tail -3
-timeout 1500 python bench.py --steps 1 --warmup 1 --cpu-sample 64 > gpurun_out/bench_first.json 2> gpurun_out/bench_first.err
+timeout 1500 python bench.py --steps 2 --warmup 1 --cpu-sample 64 $BENCH_ARGS > gpurun_out/bench_first.json 2> gpurun_out/bench_first.err
 tail -5 gpurun_out/bench_first.err
-cat gpurun_out/bench_first.json
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench_first.json'))
+print('value',round(d['value']),'e2e',round(d['e2e']['value']),'ms/step',round(d['ms_per_step']),'launches',d['gpu_launches'])
+print(d['gpu_stage_ms_per_step']); print(d['host_s_per_step']); print(d['host_counters']); print(d['roofline']); print(d['cpu_baseline']); print(d['clocks'])
+PY

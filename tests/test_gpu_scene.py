@@ -24,14 +24,14 @@ def run_and_compare(oracle, sc, **kw):
     assert np.array_equal(graph.edges["src"], committed["src"]) and np.array_equal(graph.edges["dst"], committed["dst"])
     assert np.array_equal(graph.edges["q"], committed["q"]) and np.array_equal(graph.edges["t"], committed["t"])
     assert np.array_equal(graph.edges["score"], committed["score"])
-    pgb.engine.close()
+    pgb.close()
     return pgb, ostats
 
 
-@pytest.mark.parametrize("prefetch,wave", [(True, 64), (False, 16)])
-def test_small_scene_graph_identity(oracle, prefetch, wave):
+@pytest.mark.parametrize("prefetch,wave,overlap", [(True, 64, True), (True, 1000, False), (False, 16, False)])
+def test_small_scene_graph_identity(oracle, prefetch, wave, overlap):
     sc = S.make_scene(n_views=14, n_corr=300, outlier_ratio=0.3, seed=21, n_points=900)
-    pgb, ostats = run_and_compare(oracle, sc, prefetch_fallback=prefetch, wave_size=wave)
+    pgb, ostats = run_and_compare(oracle, sc, prefetch_fallback=prefetch, wave_size=wave, overlap_fallback=overlap, fallback_wave=32)
     assert ostats["edges"] > 0
 
 
