@@ -34,7 +34,7 @@ struct Registration {
 };
 
 constexpr int kMaxChunks = 64;
-constexpr uint32_t kK5MaxSmemPts = 12288;  // 192 KB of float4
+constexpr uint32_t kK5MaxSmemPts = 11264;  // 176 KB of float4 + 22 KB of queues; also keeps point slots per thread <= 64 (mask bits)
 
 }  // namespace
 
@@ -54,6 +54,7 @@ struct pgi_ctx {
     uint64_t *d_maskOffset = nullptr;
     pgi_verdict *d_verdicts = nullptr;
     double *d_fbSols = nullptr;
+    float4 *d_fbSolsF = nullptr;
     unsigned long long *d_counters = nullptr;
     // pinned staging
     uint32_t *h_pairId = nullptr, *h_hypOffset = nullptr;
@@ -216,7 +217,8 @@ pgi_status ensureWave(pgi_ctx *ctx, const Registration &r, uint32_t n, uint32_t 
     if (n > ctx->waveCap || stride > ctx->bitsStride) {
         const uint32_t cap = std::max<uint32_t>(std::max(n, ctx->waveCap), 64);
         cudaFree(ctx->d_pairId); cudaFree(ctx->d_hypOffset); cudaFree(ctx->d_state); cudaFree(ctx->d_bits);
-        cudaFree(ctx->d_maskOffset); cudaFree(ctx->d_verdicts); cudaFree(ctx->d_fbSols); cudaFree(ctx->d_fbCounts);
+        cudaFree(ctx->d_maskOffset); cudaFree(ctx->d_verdicts); cudaFree(ctx->d_fbSols); cudaFree(ctx->d_fbCounts); cudaFree(ctx->d_fbSolsF);
+        ctx->d_fbSolsF = nullptr;
         ctx->d_pairId = ctx->d_hypOffset = ctx->d_bits = nullptr; ctx->d_state = nullptr; ctx->d_maskOffset = nullptr;
         ctx->d_verdicts = nullptr; ctx->d_fbSols = nullptr; ctx->d_fbCounts = nullptr;
         ctx->fbScratch = false;
@@ -233,6 +235,7 @@ pgi_status ensureWave(pgi_ctx *ctx, const Registration &r, uint32_t n, uint32_t 
     if ((flags & PGI_WAVE_FALLBACK) && !ctx->fbScratch) {
         CK(cudaMalloc((void **)&ctx->d_fbSols, (size_t)ctx->waveCap * kFbChunk * 90 * 8));
         CK(cudaMalloc((void **)&ctx->d_fbCounts, (size_t)ctx->waveCap * kFbChunk));
+        CK(cudaMalloc((void **)&ctx->d_fbSolsF, (size_t)ctx->waveCap * kFbChunk * 30 * sizeof(float4)));
         ctx->fbScratch = true;
     }
     if (nHyp > ctx->hypCap) {
@@ -312,7 +315,7 @@ pgi_status submitWave(pgi_ctx *ctx, const Registration &r, uint32_t n, const uin
     a.testMinInliers = testMinOverride ? testMinOverride : ctx->cfg.test_min_inliers;
     a.fbMaxIters = ctx->cfg.fallback_max_iters; a.thrMultiplier = ctx->cfg.threshold_multiplier;
     a.thrOverride = thrOverride;
-    a.fbSols = ctx->d_fbSols; a.fbCounts = ctx->d_fbCounts; a.counters = ctx->d_counters;
+    a.fbSols = ctx->d_fbSols; a.fbSolsF = ctx->d_fbSolsF; a.fbCounts = ctx->d_fbCounts; a.counters = ctx->d_counters;
 
     k1_score_hypotheses<<<n, kCtaThreads, 0, s>>>(a);
     CK(cudaEventRecord(ctx->evK1, s));
@@ -327,14 +330,16 @@ pgi_status submitWave(pgi_ctx *ctx, const Registration &r, uint32_t n, const uin
             const int chunks = (int)((ctx->cfg.fallback_max_iters + kFbChunk - 1) / kFbChunk);
             // FP32 staging area of K5: the largest pair if it fits, else 0 (those pairs take the FP64-only path)
             uint32_t smemPts = r.maxN <= kK5MaxSmemPts ? std::max<uint32_t>(r.maxN, 1) : kK5MaxSmemPts;
-            if ((size_t)smemPts * 16 > 48 * 1024)
-                CK(cudaFuncSetAttribute(k5_fallback_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)smemPts * 16)));
+            // + per-warp compaction queues: 8 warps x 32 x ceil(smemPts/256) uint16
+            const size_t k5Smem = (size_t)smemPts * 16 + (size_t)8 * 32 * ((smemPts + kCtaThreads - 1) / kCtaThreads) * 2;
+            if (k5Smem > 48 * 1024)
+                CK(cudaFuncSetAttribute(k5_fallback_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k5Smem));
             ctx->nChunks = std::min(chunks, kMaxChunks);
             for (int c = 0; c < ctx->nChunks; c++) {
                 const uint32_t threads = n * kFbChunk;
                 k4_fallback_solve<<<(threads + 63) / 64, 64, 0, s>>>(a, c);
                 CK(cudaEventRecord(ctx->evChunk[c][0], s));
-                k5_fallback_score<<<n, kCtaThreads, (size_t)smemPts * 16, s>>>(a, c, c == ctx->nChunks - 1 ? 1 : 0, smemPts);
+                k5_fallback_score<<<n, kCtaThreads, k5Smem, s>>>(a, c, c == ctx->nChunks - 1 ? 1 : 0, smemPts);
                 CK(cudaEventRecord(ctx->evChunk[c][1], s));
                 ctx->stats.launches += 2;
             }
@@ -443,7 +448,7 @@ pgi_status pgi_destroy(pgi_ctx *ctx)
     freeReg(ctx->tmp);
     cudaFree(ctx->d_pairId); cudaFree(ctx->d_hypOffset); cudaFree(ctx->d_bits); cudaFree(ctx->d_hyp);
     cudaFree(ctx->d_state); cudaFree(ctx->d_masks); cudaFree(ctx->d_fbCounts); cudaFree(ctx->d_maskOffset);
-    cudaFree(ctx->d_verdicts); cudaFree(ctx->d_fbSols); cudaFree(ctx->d_counters);
+    cudaFree(ctx->d_verdicts); cudaFree(ctx->d_fbSols); cudaFree(ctx->d_fbSolsF); cudaFree(ctx->d_counters);
     cudaFreeHost(ctx->h_pairId); cudaFreeHost(ctx->h_hypOffset); cudaFreeHost(ctx->h_hyp);
     cudaFreeHost(ctx->h_maskOffset); cudaFreeHost(ctx->h_verdicts); cudaFreeHost(ctx->h_counters);
     cudaEvent_t evs[] = {ctx->evStart, ctx->evK1, ctx->evK2, ctx->evK3, ctx->evFbEnd};

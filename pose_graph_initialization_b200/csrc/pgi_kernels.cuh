@@ -83,6 +83,7 @@ struct WaveArgs {
     double thrOverride;  // > 0: tester threshold given explicitly (pgi_test_pose)
     // fallback scratch
     double *fbSols;     // n x kFbChunk x 90
+    float4 *fbSolsF;    // n x kFbChunk x 10 models x 3 float4 (FP32 copy for the certificate)
     uint8_t *fbCounts;  // n x kFbChunk
     unsigned long long *counters;  // [0] corr evals, [1] fallback pairs, [2] fallback models
 };
@@ -333,6 +334,13 @@ __global__ void __launch_bounds__(64) k4_fallback_solve(WaveArgs a, int chunk)
     double *out = a.fbSols + ((size_t)w * kFbChunk + j) * 90;
     const int n = fivePoint<false>(x1, x2, out, 10, kDkMaxSweeps, kDkTolSq);
     a.fbCounts[(size_t)w * kFbChunk + j] = (uint8_t)n;
+    float4 *outF = a.fbSolsF + ((size_t)w * kFbChunk + j) * 30;
+    for (int q = 0; q < n; q++) {
+        const double *e = out + q * 9;
+        outF[q * 3 + 0] = make_float4((float)e[0], (float)e[1], (float)e[2], (float)e[3]);
+        outF[q * 3 + 1] = make_float4((float)e[4], (float)e[5], (float)e[6], (float)e[7]);
+        outF[q * 3 + 2] = make_float4((float)e[8], 0.f, 0.f, 0.f);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -340,9 +348,9 @@ __global__ void __launch_bounds__(64) k4_fallback_solve(WaveArgs a, int chunk)
 // oracle/pgo_fallback.hpp): terms are produced by IEEE FP64 operations, converted to integers once and
 // added with integer arithmetic, so warps/CTAs may reduce in any order (shuffles, shared-memory atomics).
 // ---------------------------------------------------------------------------------------------
+constexpr int kBatch = 8;                     // fallback iterations scored between two decision points of K5
 constexpr double kCostOne = 4294967296.0;     // fixed-point MSAC cost of an outlier (2^32)
 constexpr double kLsScale = 1099511627776.0;  // 2^40: fixed-point scale of the normal-equation products
-constexpr int kQueueCap = 64;                 // per-warp queue of correspondences awaiting the exact FP64 path
 
 __device__ __forceinline__ unsigned long long warpSumU64(unsigned long long v)
 {
@@ -381,69 +389,90 @@ __device__ __forceinline__ void exactTerm(const double4 *rows, uint32_t i, const
     inl += (rr < thrSq) ? 1u : 0u;
 }
 
-// Score one model over the pair: thread t handles the points t, t + 256, ...
+// Score up to two models in one pass over the pair: thread t handles the points t, t + 256, ...
 // FP32 (FMA, shared-memory float4 copy) only CERTIFIES that a correspondence is far outside the truncation band
 // — then its term is exactly 2^32 and it is no inlier.  With r = x2h^T E x1h the Sampson numerator and
 // denom = |(E^T x2h)_xy|^2 + |(E x1h)_xy|^2 <= ||E||_F^2 (|x1h|^2 + |x2h|^2) = D  (models have unit Frobenius norm):
 //     |r_f32 - r| <= 4.2e-7 B < eAbs := 1e-6 max_i B_i,  B = (|x1|+|y1|+1)(|x2|+|y2|+1)   (input + 8 FMA roundings)
 //  => |r_f32| > rOut := sqrt(truncSq max_i D_i)(1 + 2^-10) + eAbs   implies   r^2 / denom > truncSq.
-// One 8-FMA chain and one compare per (model, correspondence).  Everything not certified (inliers, near-band
-// points, NaNs) is queued per warp and evaluated DENSELY, 32 at a time, by the exact FP64 path, so the FP64 pipe
-// only sees the few percent of evaluations that can matter.  Returns the warp's partial (cost, inliers) in lane 0.
-template <bool USE_F32>
-__device__ __forceinline__ void scoreModelWarp(const double4 *rows, const float4 *pts, uint32_t N, const double *Eg /*9, global/shared*/,
-                                               double thrSq, double truncSq, double invT, F32Consts fc, uint32_t *queue /*kQueueCap*/,
-                                               unsigned long long &costOut, uint32_t &inlOut)
+// Hot loop: one LDS.128, an 8-FMA chain and one compare per (model, correspondence); the uncertain ones only set a
+// bit in a per-thread mask.  Afterwards each warp compacts its masks into a shared-memory queue (one prefix scan)
+// and the exact FP64 path runs DENSELY, 32 queued correspondences at a time, so the FP64 pipe only sees the few
+// percent of evaluations that can matter.  Returns the warp's partial (cost, inliers) per model in lane 0.
+__device__ __forceinline__ void exactQueue(const double4 *rows, const double *Eg, unsigned long long mask, uint16_t *queue,
+                                           double thrSq, double truncSq, double invT, unsigned long long &cost, uint32_t &inl)
 {
     const int lane = threadIdx.x & 31;
-    unsigned long long cost = 0;
-    uint32_t inl = 0, nOut = 0;
-    const double *Ed = Eg;  // the exact path re-reads the model (L1/shared) instead of pinning 18 registers
-    if (USE_F32) {
-        float E[9];
+    const uint32_t mine = (uint32_t)__popcll(mask);
+    uint32_t incl = mine;
 #pragma unroll
-        for (int k = 0; k < 9; k++) E[k] = (float)Eg[k];
-        uint32_t qn = 0;  // warp-uniform
-        const uint32_t nRound = (N + kCtaThreads - 1) / kCtaThreads * kCtaThreads;
-        for (uint32_t i = threadIdx.x; i < nRound; i += kCtaThreads) {
-            bool unsure = false;
-            if (i < N) {
-                const float4 p = pts[i];
-                const float rxc = fmaf(E[0], p.z, fmaf(E[3], p.w, E[6]));
-                const float ryc = fmaf(E[1], p.z, fmaf(E[4], p.w, E[7]));
-                const float rwc = fmaf(E[2], p.z, fmaf(E[5], p.w, E[8]));
-                const float r = fmaf(p.x, rxc, fmaf(p.y, ryc, rwc));
-                const bool outside = fabsf(r) > fc.rOut;  // false for NaN
-                nOut += outside ? 1u : 0u;
-                unsure = !outside;
-            }
-            const uint32_t m = __ballot_sync(0xffffffffu, unsure);
-            if (m) {
-                if (unsure) queue[qn + __popc(m & ((1u << lane) - 1u))] = i;
-                qn += __popc(m);
-                __syncwarp();
-                if (qn >= 32) {
-                    const uint32_t idx = queue[lane];
-                    exactTerm(rows, idx, Ed, thrSq, truncSq, invT, cost, inl);
-                    const uint32_t rest = qn - 32;  // < 32
-                    const uint32_t moved = lane < rest ? queue[32 + lane] : 0u;
-                    __syncwarp();
-                    if (lane < rest) queue[lane] = moved;
-                    qn = rest;
-                    __syncwarp();
-                }
-            }
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;  // warp-uniform
+    uint32_t pos = incl - mine;
+    while (mask) {
+        const int j = __ffsll((long long)mask) - 1;
+        mask &= mask - 1;
+        queue[pos++] = (uint16_t)(threadIdx.x + j * kCtaThreads);
+    }
+    __syncwarp();
+    for (uint32_t base = 0; base < total; base += 32)
+        if (base + lane < total) exactTerm(rows, queue[base + lane], Eg, thrSq, truncSq, invT, cost, inl);
+    __syncwarp();
+}
+
+template <bool USE_F32>
+__device__ __forceinline__ void scoreModelsWarp(const double4 *rows, const float4 *pts, uint32_t N, const double *Eg0,
+                                                const double *Eg1 /*null: one model*/, const float4 *Ef /*3 float4 per model*/,
+                                                double thrSq, double truncSq, double invT, float rOut, uint16_t *queue,
+                                                unsigned long long costOut[2], uint32_t inlOut[2])
+{
+    unsigned long long cost0 = 0, cost1 = 0;
+    uint32_t inl0 = 0, inl1 = 0;
+    const bool two = Eg1 != nullptr;
+    if (USE_F32) {
+        const float4 a0 = Ef[0], a1 = Ef[1], a2 = Ef[2];  // e0..e8 of model 0
+        float4 b0 = a0, b1 = a1, b2 = a2;
+        if (two) { b0 = Ef[3]; b1 = Ef[4]; b2 = Ef[5]; }
+        unsigned long long m0 = 0, m1 = 0;
+        uint32_t j = 0;
+#pragma unroll 4
+        for (uint32_t i = threadIdx.x; i < N; i += kCtaThreads, ++j) {
+            const float4 p = pts[i];
+            // model 0: E = [a0.x a0.y a0.z; a0.w a1.x a1.y; a1.z a1.w a2.x]
+            const float rxc0 = fmaf(a0.x, p.z, fmaf(a0.w, p.w, a1.z));
+            const float ryc0 = fmaf(a0.y, p.z, fmaf(a1.x, p.w, a1.w));
+            const float rwc0 = fmaf(a0.z, p.z, fmaf(a1.y, p.w, a2.x));
+            const float r0 = fmaf(p.x, rxc0, fmaf(p.y, ryc0, rwc0));
+            const float rxc1 = fmaf(b0.x, p.z, fmaf(b0.w, p.w, b1.z));
+            const float ryc1 = fmaf(b0.y, p.z, fmaf(b1.x, p.w, b1.w));
+            const float rwc1 = fmaf(b0.z, p.z, fmaf(b1.y, p.w, b2.x));
+            const float r1 = fmaf(p.x, rxc1, fmaf(p.y, ryc1, rwc1));
+            m0 |= (unsigned long long)(!(fabsf(r0) > rOut)) << j;  // NaN stays uncertain
+            m1 |= (unsigned long long)(!(fabsf(r1) > rOut)) << j;
         }
-        if (qn) {
-            if ((uint32_t)lane < qn) exactTerm(rows, queue[lane], Ed, thrSq, truncSq, invT, cost, inl);
-            __syncwarp();
+        const uint32_t nPts = N > threadIdx.x ? (N - threadIdx.x + kCtaThreads - 1) / kCtaThreads : 0u;
+        cost0 = (unsigned long long)(nPts - (uint32_t)__popcll(m0)) << 32;
+        exactQueue(rows, Eg0, m0, queue, thrSq, truncSq, invT, cost0, inl0);
+        if (two) {
+            cost1 = (unsigned long long)(nPts - (uint32_t)__popcll(m1)) << 32;
+            exactQueue(rows, Eg1, m1, queue, thrSq, truncSq, invT, cost1, inl1);
         }
     } else {
-        for (uint32_t i = threadIdx.x; i < N; i += kCtaThreads) exactTerm(rows, i, Ed, thrSq, truncSq, invT, cost, inl);
+        for (uint32_t i = threadIdx.x; i < N; i += kCtaThreads) {
+            exactTerm(rows, i, Eg0, thrSq, truncSq, invT, cost0, inl0);
+            if (two) exactTerm(rows, i, Eg1, thrSq, truncSq, invT, cost1, inl1);
+        }
     }
-    cost += (unsigned long long)nOut << 32;
-    costOut = warpSumU64(cost);
-    inlOut = __reduce_add_sync(0xffffffffu, inl);
+    costOut[0] = warpSumU64(cost0);
+    inlOut[0] = __reduce_add_sync(0xffffffffu, inl0);
+    if (two) {
+        costOut[1] = warpSumU64(cost1);
+        inlOut[1] = __reduce_add_sync(0xffffffffu, inl1);
+    }
 }
 
 // Symmetric 9x9 cyclic Jacobi, eigenvector of the smallest eigenvalue.  Same rotation sequence and the same
@@ -578,7 +607,8 @@ __device__ inline void lsRefitBlock(const double4 *rows, uint32_t N, const doubl
 // matters), their fixed-point costs land in shared memory through atomics, one barrier, then thread 0 decides.
 // ---------------------------------------------------------------------------------------------
 template <bool USE_F32>
-__device__ __forceinline__ void k5Body(const WaveArgs &a, int chunk, int lastChunk, uint32_t w, float4 *sPts)
+__device__ __forceinline__ void k5Body(const WaveArgs &a, int chunk, int lastChunk, uint32_t w, float4 *sPts, uint16_t *sQueueAll,
+                                       uint32_t queueStride)
 {
     SlotState &st = a.state[w];
     const uint32_t flags0 = st.flags;
@@ -593,9 +623,10 @@ __device__ __forceinline__ void k5Body(const WaveArgs &a, int chunk, int lastChu
     const double invT = 1.0 / truncSq;
 
     __shared__ uint32_t sWarpU[8];
-    __shared__ uint32_t sQueue[kCtaThreads / 32][kQueueCap];
-    __shared__ unsigned long long sCost[2][10];
-    __shared__ uint32_t sInl[2][10];
+    __shared__ float4 sElsF[3];
+    __shared__ unsigned long long sCost[kBatch][10], sLoCost;
+    __shared__ uint32_t sInl[kBatch][10], sLoInl, sModels;
+    __shared__ int sNextB;
     __shared__ float sMaxB[8], sMaxD[8];
     __shared__ long long sAcc[45];
     __shared__ double sM[81], sV[81], sEls[9], sBestE[9];
@@ -603,6 +634,7 @@ __device__ __forceinline__ void k5Body(const WaveArgs &a, int chunk, int lastChu
     __shared__ int sBestInl, sMaxIters, sOk, sUpdated, sHave;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint16_t *sQueue = sQueueAll + (size_t)warp * queueStride;  // this warp's compaction queue (32 x points-per-thread)
     if (threadIdx.x == 0) {
         sBestCost = st.bestCost;
         sBestInl = st.bestInl;
@@ -610,7 +642,8 @@ __device__ __forceinline__ void k5Body(const WaveArgs &a, int chunk, int lastChu
         sHave = st.bestCost != ~0ull ? 1 : 0;
         for (int k = 0; k < 9; k++) sBestE[k] = st.bestE[k];
     }
-    if (threadIdx.x < 20) { sCost[threadIdx.x / 10][threadIdx.x % 10] = 0; sInl[threadIdx.x / 10][threadIdx.x % 10] = 0; }
+    if (threadIdx.x < kBatch * 10) { sCost[threadIdx.x / 10][threadIdx.x % 10] = 0; sInl[threadIdx.x / 10][threadIdx.x % 10] = 0; }
+    if (threadIdx.x == 0) sModels = 0;
     const bool active = (flags0 & ST_FB_ACTIVE) != 0;
     F32Consts fc{3.0e38f};
     if (USE_F32 && active) {
@@ -641,69 +674,92 @@ __device__ __forceinline__ void k5Body(const WaveArgs &a, int chunk, int lastChu
         fc.rOut = (rOut < 1e30 && rOut == rOut) ? (float)(rOut * (1.0 + 1.1920928955078125e-7)) : 3.0e38f;
     }
     uint32_t models = 0;
-    int parity = 0;
     int it = st.it;
     if (active) {
         const uint16_t *itTab = a.itersTab + a.itersTabOff[st.tableIdx];
         const int itEnd = (chunk + 1) * kFbChunk;
-        for (; it < itEnd && it < sMaxIters; ++it) {
-            const int j = it - chunk * kFbChunk;
-            const int ns = a.fbCounts[(size_t)w * kFbChunk + j];
-            const double *sols = a.fbSols + ((size_t)w * kFbChunk + j) * 90;
-            for (int q = 0; q < ns; q++) {
-                unsigned long long c;
-                uint32_t n;
-                scoreModelWarp<USE_F32>(rows, sPts, N, sols + q * 9, thrSq, truncSq, invT, fc, sQueue[warp], c, n);
-                if (lane == 0) {
-                    atomicAdd(&sCost[parity][q], c);
-                    atomicAdd(&sInl[parity][q], n);
-                }
-            }
-            models += ns;
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                int upd = 0;
-                for (int q = 0; q < ns; q++) {
-                    if (sCost[parity][q] < sBestCost) {
-                        sBestCost = sCost[parity][q];
-                        sBestInl = (int)sInl[parity][q];
-                        for (int k = 0; k < 9; k++) sBestE[k] = sols[q * 9 + k];
-                        upd = 1;
-                        sHave = 1;
+        while (it < itEnd && it < sMaxIters) {
+            // ---- phase 1: score every model of the next kBatch iterations (pure functions of the models) ----------
+            int nb = itEnd - it < kBatch ? itEnd - it : kBatch;
+            nb = sMaxIters - it < nb ? sMaxIters - it : nb;
+            for (int bI = 0; bI < nb; bI++) {
+                const int j = it + bI - chunk * kFbChunk;
+                const int ns = a.fbCounts[(size_t)w * kFbChunk + j];
+                const double *sols = a.fbSols + ((size_t)w * kFbChunk + j) * 90;
+                const float4 *solsF = a.fbSolsF + ((size_t)w * kFbChunk + j) * 30;
+                for (int q = 0; q < ns; q += 2) {
+                    unsigned long long c[2];
+                    uint32_t n[2];
+                    const bool two = q + 1 < ns;
+                    scoreModelsWarp<USE_F32>(rows, sPts, N, sols + q * 9, two ? sols + (q + 1) * 9 : nullptr, solsF + q * 3, thrSq,
+                                             truncSq, invT, fc.rOut, sQueue, c, n);
+                    if (lane == 0) {
+                        atomicAdd(&sCost[bI][q], c[0]);
+                        atomicAdd(&sInl[bI][q], n[0]);
+                        if (two) {
+                            atomicAdd(&sCost[bI][q + 1], c[1]);
+                            atomicAdd(&sInl[bI][q + 1], n[1]);
+                        }
                     }
-                    sCost[parity][q] = 0;  // ready for the iteration after next (a barrier away)
-                    sInl[parity][q] = 0;
                 }
-                sUpdated = upd;
             }
-            parity ^= 1;
             __syncthreads();
-            if (sUpdated) {
+            // ---- phase 2: the sequential best-so-far walk, LO refits interleaved exactly where a sequential
+            //      RANSAC would run them; iterations beyond a shrunken maxIters are discarded unscored-in-effect ----
+            if (threadIdx.x == 0) sNextB = 0;
+            for (;;) {
+                if (threadIdx.x == 0) {
+                    int bI = sNextB, upd = 0;
+                    for (; bI < nb && it + bI < sMaxIters && !upd; ++bI) {
+                        const int j = it + bI - chunk * kFbChunk;
+                        const int ns = a.fbCounts[(size_t)w * kFbChunk + j];
+                        const double *sols = a.fbSols + ((size_t)w * kFbChunk + j) * 90;
+                        for (int q = 0; q < ns; q++)
+                            if (sCost[bI][q] < sBestCost) {
+                                sBestCost = sCost[bI][q];
+                                sBestInl = (int)sInl[bI][q];
+                                for (int k = 0; k < 9; k++) sBestE[k] = sols[q * 9 + k];
+                                upd = 1;
+                                sHave = 1;
+                            }
+                        sModels += ns;
+                    }
+                    sNextB = bI;
+                    sUpdated = upd;
+                }
+                __syncthreads();
+                if (!sUpdated) break;
                 for (int r = 0; r < kLoRounds; r++) {
                     double Eb[9];
 #pragma unroll
                     for (int k = 0; k < 9; k++) Eb[k] = sBestE[k];
                     lsRefitBlock(rows, N, Eb, thrSq, sAcc, sM, sV, sWarpU, sEls, &sOk);
                     if (!sOk) break;
-                    unsigned long long c;
-                    uint32_t n;
-                    scoreModelWarp<USE_F32>(rows, sPts, N, sEls, thrSq, truncSq, invT, fc, sQueue[warp], c, n);
-                    if (lane == 0) {
-                        atomicAdd(&sCost[parity][0], c);
-                        atomicAdd(&sInl[parity][0], n);
+                    if (threadIdx.x == 0) {
+                        sElsF[0] = make_float4((float)sEls[0], (float)sEls[1], (float)sEls[2], (float)sEls[3]);
+                        sElsF[1] = make_float4((float)sEls[4], (float)sEls[5], (float)sEls[6], (float)sEls[7]);
+                        sElsF[2] = make_float4((float)sEls[8], 0.f, 0.f, 0.f);
+                        sLoCost = 0;
+                        sLoInl = 0;
                     }
-                    models++;
+                    __syncthreads();
+                    unsigned long long c[2];
+                    uint32_t n[2];
+                    scoreModelsWarp<USE_F32>(rows, sPts, N, sEls, nullptr, sElsF, thrSq, truncSq, invT, fc.rOut, sQueue, c, n);
+                    if (lane == 0) {
+                        atomicAdd(&sLoCost, c[0]);
+                        atomicAdd(&sLoInl, n[0]);
+                    }
                     __syncthreads();
                     if (threadIdx.x == 0) {
-                        if (sCost[parity][0] < sBestCost) {
-                            sBestCost = sCost[parity][0];
-                            sBestInl = (int)sInl[parity][0];
+                        sModels += 1;
+                        if (sLoCost < sBestCost) {
+                            sBestCost = sLoCost;
+                            sBestInl = (int)sLoInl;
                             for (int k = 0; k < 9; k++) sBestE[k] = sEls[k];
                             sOk = 1;
                         } else
                             sOk = 0;
-                        sCost[parity][0] = 0;
-                        sInl[parity][0] = 0;
                     }
                     __syncthreads();
                     if (!sOk) break;
@@ -714,9 +770,16 @@ __device__ __forceinline__ void k5Body(const WaveArgs &a, int chunk, int lastChu
                 }
                 __syncthreads();
             }
+            // consumed iterations: sNextB (all nb unless maxIters shrank below it + nb)
+            it += sNextB;
+            __syncthreads();
+            if (threadIdx.x < kBatch * 10) { sCost[threadIdx.x / 10][threadIdx.x % 10] = 0; sInl[threadIdx.x / 10][threadIdx.x % 10] = 0; }
+            __syncthreads();
+            if (sNextB < nb) break;  // maxIters reached inside the batch
         }
     }
     __syncthreads();
+    if (threadIdx.x == 0) models = sModels;
     const bool done = !active || it >= sMaxIters || lastChunk;
     // finalise: mask == sampson^2(E_final) < thr^2 and its count
     uint32_t finalInl = 0;
@@ -767,10 +830,13 @@ __global__ void __launch_bounds__(kCtaThreads, 3) k5_fallback_score(WaveArgs a, 
     if (!(a.state[w].flags & ST_NEED_FB)) return;
     const uint32_t pid = a.pairId[w];
     const uint32_t N = (uint32_t)(a.offset[pid + 1] - a.offset[pid]);
+    // dynamic shared memory: smemPts float4 points, then 8 per-warp queues of 32 * ceil(smemPts / 256) uint16 indices
+    const uint32_t queueStride = 32u * ((smemPts + kCtaThreads - 1) / kCtaThreads);
+    uint16_t *sQueueAll = reinterpret_cast<uint16_t *>(sPts + smemPts);
     if (N <= smemPts)
-        k5Body<true>(a, chunk, lastChunk, w, sPts);
+        k5Body<true>(a, chunk, lastChunk, w, sPts, sQueueAll, queueStride);
     else
-        k5Body<false>(a, chunk, lastChunk, w, sPts);  // pair too large to stage: exact FP64 for every point
+        k5Body<false>(a, chunk, lastChunk, w, sPts, sQueueAll, queueStride);  // pair too large to stage: exact FP64 for every point
 }
 
 // Whole-CTA E -> candidates -> triangulation vote (pose_utils.h:172-240).  Results in shared memory.
