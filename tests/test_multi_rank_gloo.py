@@ -1,0 +1,81 @@
+"""N > 1 host path on CPU: two ranks (gloo) shard the pairs by owner, each produces verdicts for the wave items it owns
+(oracle stand-in for the engine — tests only), the 160-byte records are all-gathered, and BOTH ranks must commit the
+pose graph the single-process sequential oracle commits (SPMD host)."""
+import os
+import sys
+
+import numpy as np
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT); sys.path.insert(0, HERE)
+    import torch.distributed as dist
+
+    from oracle import pgo_oracle as O
+    from oracle_engine import OracleEngine
+    from pose_graph_initialization_b200 import builder as B
+    from pose_graph_initialization_b200 import scene as S
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sc = S.make_scene(n_views=9, n_corr=150, outlier_ratio=0.3, seed=11, n_points=500)
+    P = len(sc["pair_views"])
+    bounds = B.owner_ranges(P, world)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    sub = B.shard_scene(sc, lo, hi)
+    assert len(sub["pair_views"]) == hi - lo and int(sub["m_offset"][-1]) == len(sub["matches"])
+    eng = OracleEngine(O, sc)  # verdicts only for owned pairs
+    host = B.HostBuilder(sc, similarity_threshold=0.0, host_threads=2, lazy_fallback=False)
+    # sharded prefetch + one all-gather
+    mine = np.zeros(hi - lo, dtype=B.VERDICT_DTYPE)
+    for k, p in enumerate(range(lo, hi)):
+        mine[k] = eng.verdict(p, None, path=False, fallback=True)
+    parts = B.allgather_verdicts(mine, [int(bounds[r + 1] - bounds[r]) for r in range(world)])
+    host.set_fallback_verdicts(np.concatenate(parts))
+    while host.remaining() > 0:
+        items = host.next_wave(64)
+        todo = np.nonzero(items["need_gpu"])[0]
+        own = B.owner_of(items["pair_id"][todo], bounds)
+        local = eng.run_items(items[todo[own == rank]], path=True, fallback=False)
+        parts = B.allgather_verdicts(local, [int(np.count_nonzero(own == r)) for r in range(world)])
+        verdicts = np.zeros(len(todo), dtype=B.VERDICT_DTYPE)
+        for r in range(world):
+            verdicts[np.nonzero(own == r)[0]] = parts[r]
+        host.commit_wave(verdicts)
+    edges = host.edges()
+    olog, ostats = O.run_scene(sc, sim_threshold=0.0)
+    committed = olog[olog["committed"] > 0]
+    ok = (len(edges) == ostats["edges"] and np.array_equal(edges["src"], committed["src"])
+          and np.array_equal(edges["q"], committed["q"]) and np.array_equal(edges["score"], committed["score"]))
+    ret[rank] = (bool(ok), eng.calls, len(edges))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_commit_the_sequential_graph():
+    world = 2
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=600)
+        assert p.exitcode == 0
+    assert ret[0][0] and ret[1][0]
+    assert ret[0][2] == ret[1][2] > 0
+    # the work really was sharded: neither rank verified everything
+    assert ret[0][1] > 0 and ret[1][1] > 0
+
+
+def test_owner_ranges_and_shards():
+    from pose_graph_initialization_b200 import builder as B
+
+    b = B.owner_ranges(10, 4)
+    assert list(b) == [0, 2, 5, 7, 10]
+    assert list(B.owner_of([0, 1, 2, 4, 5, 9], b)) == [0, 0, 1, 1, 2, 3]
