@@ -95,6 +95,8 @@ int pgo_find_essential_ransac_inf(const double *pts, int count, double *E, uint8
     return n;
 }
 
+int pgo_dbg_last_dk_sweeps() { return cvx::lastDkSweeps(); }
+
 // ---- Eigen-owned stages --------------------------------------------------------------------------
 void pgo_eigen_svd3(const double *A, double *U, double *V, double *S) { eig::jacobiSvd<3>(A, U, V, S); }
 void pgo_eigen_svd4(const double *A, double *U, double *V, double *S) { eig::jacobiSvd<4>(A, U, V, S); }

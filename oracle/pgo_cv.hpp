@@ -247,6 +247,7 @@ inline bool invert10(const double A1[100], double inv[100])
 
 // ---- cv::solvePoly (core/src/mathfuncs.cpp) — Durand-Kerner, Gauss-Seidel order ----------------
 struct Cx { double re, im; };
+inline int &lastDkSweeps() { static thread_local int v = 0; return v; }  // diagnostics only
 inline Cx cmul(Cx a, Cx b) { return Cx{a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
 inline Cx cadd(Cx a, Cx b) { return Cx{a.re + b.re, a.im + b.im}; }
 inline Cx csub(Cx a, Cx b) { return Cx{a.re - b.re, a.im - b.im}; }
@@ -292,8 +293,9 @@ inline int solvePoly(const double *c, int n0, Cx *roots, int maxIters = 1000, do
             roots[i] = csub(p, num);
             maxDiffSq = std::max(maxDiffSq, num.re * num.re + num.im * num.im);
         }
-        if (maxDiffSq <= tolSq) break;
+        if (maxDiffSq <= tolSq) { ++iter; break; }
     }
+    lastDkSweeps() = iter;
     const double verySmallEps = 1e-100;
     for (i = 0; i < n; i++)
         if (std::fabs(roots[i].im) < verySmallEps) roots[i].im = 0;
@@ -517,6 +519,13 @@ inline int fivePointKernel(const double *x1, const double *x2, int npts, double 
 // error is an inlier) as called at pose_graph_builder.h:1013-1020.  pts: count x 4 [x1 y1 x2 y2].
 // Returns number of 3x3 models written to E (0 = failure, >1 only when count == 5);
 // mask (count bytes) is written only on success, as OpenCV does.
+// Durand-Kerner stopping rule used on this path.  cv::solvePoly burns maxIters = 1000 sweeps unless a correction is
+// exactly 0; the sweeps after convergence only jitter the last bit.  The restatement stops at max |correction|^2 <=
+// kLegacyDkTolSq = 1e-22 (the next error is then ~1e-22 by quadratic convergence; or cv's 1000-sweep cap): same Gauss-Seidel trajectory, hence the same root -> index assignment
+// and the same "first admissible root"; values agree with cv2 to ~1e-13 like the rest of the kernel
+// (tests/test_oracle_golden.py pins count, order and values against cv2.findEssentialMat).
+constexpr double kLegacyDkTolSq = 1e-22;
+
 struct LegacyRansacInfo {
     int iterations = 0;       // samples drawn
     int sample[5] = {0, 0, 0, 0, 0};
@@ -532,7 +541,7 @@ inline int findEssentialMatRansacInf(const double *pts, int count, double *E /*u
             x1[2 * i] = pts[4 * i]; x1[2 * i + 1] = pts[4 * i + 1];
             x2[2 * i] = pts[4 * i + 2]; x2[2 * i + 1] = pts[4 * i + 3];
         }
-        int n = fivePointKernel(x1, x2, 5, E);
+        int n = fivePointKernel(x1, x2, 5, E, 1000, kLegacyDkTolSq);
         if (n <= 0) return 0;
         if (mask) std::memset(mask, 1, count);
         return n;
@@ -554,7 +563,7 @@ inline int findEssentialMatRansacInf(const double *pts, int count, double *E /*u
             info->iterations = iter + 1;
             for (int i = 0; i < 5; i++) info->sample[i] = idx[i];
         }
-        const int nmodels = fivePointKernel(x1, x2, 5, models);
+        const int nmodels = fivePointKernel(x1, x2, 5, models, 1000, kLegacyDkTolSq);
         if (nmodels <= 0) continue;
         for (int mi = 0; mi < nmodels; mi++) {
             // findInliers with thresh^2 = +inf: err <= inf unless NaN (EMEstimatorCallback::computeError)

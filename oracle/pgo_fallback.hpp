@@ -38,7 +38,7 @@ constexpr double kConfidence = 0.99;  // pose_graph_builder.h:1042
 constexpr int kLoRounds = 4;          // max least-squares refits after each new best model
 constexpr int kLoMinInliers = 9;      // need > 8 points for the linear fit
 constexpr int kDkMaxSweeps = 200;     // Durand-Kerner sweeps for the fallback's minimal solver
-constexpr double kDkTolSq = 1e-26;    // stop when max |correction|^2 <= this
+constexpr double kDkTolSq = 1e-22;    // stop when max |correction|^2 <= this (quadratic convergence: the next error is ~1e-22)
 constexpr double kCostOne = 4294967296.0;       // MSAC term of an outlier in fixed point (2^32)
 constexpr double kLsScale = 1099511627776.0;    // 2^40: fixed-point scale of the normal-equation products
 

@@ -23,7 +23,8 @@ constexpr int kFbChunk = 125;         // fallback iterations solved per K4 launc
 constexpr int kLoRounds = 4;
 constexpr int kLoMinInliers = 9;
 constexpr int kDkMaxSweeps = 200;
-constexpr double kDkTolSq = 1e-26;
+constexpr double kDkTolSq = 1e-22;
+constexpr double kLegacyDkTolSq = 1e-22;  // K2: Durand-Kerner stops at convergence instead of cv::solvePoly's fixed 1000 sweeps
 
 enum : uint32_t {
     ST_HAVE_HYP = 1u,       // pair had >= 1 hypothesis in this wave
@@ -233,8 +234,9 @@ __device__ inline uint32_t selectRank(const uint32_t *bits, uint32_t nWords, uin
 // ---------------------------------------------------------------------------------------------
 // K2: legacy cv::findEssentialMat(RANSAC, threshold = DBL_MAX) on the inliers of the hypothesis:
 // MWC RNG(2^64-1) draws 5 distinct ranks in [0,k); the first solution of the first sample that yields
-// a model wins and every point is its inlier.  One thread per wave pair; the
-// 1000-sweep Durand-Kerner chain is latency-bound, so waves should be large.
+// a model wins and every point is its inlier.  One thread per wave pair.  The Durand-Kerner
+// root solve stops at convergence (kLegacyDkTolSq) rather than burning cv::solvePoly's 1000 fixed sweeps — same
+// trajectory, same root order, values equal to cv2's to ~1e-13 (the oracle does the same and is pinned to cv2).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(64) k2_fivept_first_solution(WaveArgs a)
 {
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(64) k2_fivept_first_solution(WaveArgs a)
                 const double4 c = rows[selectRank(bits, nWords, i)];
                 x1[2 * i] = c.x; x1[2 * i + 1] = c.y; x2[2 * i] = c.z; x2[2 * i + 1] = c.w;
             }
-            found = fivePoint<true>(x1, x2, E, 1, 1000, 0.0) > 0;
+            found = fivePoint<false>(x1, x2, E, 1, 1000, kLegacyDkTolSq) > 0;
         } else {
             CvRng rng((uint64_t)-1);
             for (int iter = 0; iter < 1000 && !found; iter++) {
@@ -279,7 +281,7 @@ __global__ void __launch_bounds__(64) k2_fivept_first_solution(WaveArgs a)
                     const double4 c = rows[selectRank(bits, nWords, (uint32_t)idx_i)];
                     x1[2 * i] = c.x; x1[2 * i + 1] = c.y; x2[2 * i] = c.z; x2[2 * i + 1] = c.w;
                 }
-                found = fivePoint<true>(x1, x2, E, 1, 1000, 0.0) > 0;
+                found = fivePoint<false>(x1, x2, E, 1, 1000, kLegacyDkTolSq) > 0;
             }
         }
         if (!(flags & ST_NEED_5PT)) {
