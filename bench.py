@@ -118,7 +118,7 @@ def run_reference(args, rank, world):
         return
     scene = make_scene(args.config)
     cores = os.cpu_count() or 1
-    sample = max(4 * cores, 64)
+    sample = args.cpu_sample or 128 * cores  # ~5 s of all-core CPU work per step
     for _ in range(args.warmup):
         cpu_leg(scene, max(cores, 8))
     tot_p, tot_s, last = 0, 0.0, None
@@ -150,7 +150,7 @@ def main():
     ap.add_argument("--config", default="cfg2_300v")
     ap.add_argument("--wave", type=int, default=1024)
     ap.add_argument("--no-overlap", action="store_true", help="prefetch the fallback before the waves instead of concurrently")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the cpu_baseline sample (0 = 8 x cores)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the cpu_baseline sample (0 = 256 x cores, ~10-15 s)")
     ap.add_argument("--lazy", action="store_true", help="run the fallback lazily inside the waves instead of prefetching it")
     args = ap.parse_args()
 
@@ -261,7 +261,7 @@ def main():
     line = None
     if rank == 0:
         cores = os.cpu_count() or 1
-        cpu = cpu_leg(scene, args.cpu_sample or 8 * cores)
+        cpu = cpu_leg(scene, args.cpu_sample or 256 * cores)  # ~10-15 s of all-core CPU work
         line = {
             "metric": "image_pairs_verified_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_resident / K, "higher_is_better": True, "scaling": "strong",

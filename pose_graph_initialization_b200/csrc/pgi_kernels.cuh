@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(64) k2_fivept_first_solution(WaveArgs a)
 // The uniform sampler's sequence depends on N only (persistent-pool partial Fisher-Yates driven by
 // cv::RNG(0)), so the samples come from a per-N table built at registration.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) k4_fallback_solve(WaveArgs a, int chunk)
+__global__ void __launch_bounds__(64, 6) k4_fallback_solve(WaveArgs a, int chunk)
 {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t w = g / kFbChunk, j = g % kFbChunk;
@@ -888,7 +888,7 @@ __device__ inline void decomposeVoteBlock(const double E[9], const double4 *rows
 // local).  FP64-pipe bound.  Thread 0 picks the first maximum, converts to a unit quaternion and
 // packs the 160-byte verdict.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kCtaThreads) k3_decompose_vote(WaveArgs a)
+__global__ void __launch_bounds__(kCtaThreads, 2) k3_decompose_vote(WaveArgs a)
 {
     const uint32_t w = blockIdx.x;
     if (w >= a.n) return;
