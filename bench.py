@@ -25,6 +25,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
+# ncu --set full on k5_fallback_score (profiles/): (dram__bytes_read + dram__bytes_write) / pairs of the launch
+NCU_K5_DRAM_BYTES_PER_PAIR_LAUNCH = 123_000
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -138,10 +142,23 @@ def run_reference(args, rank, world):
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+def emit(line):
+    """Exactly one JSON line on the real stdout (NCCL/torch banners are diverted to stderr, see main)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
 
 
 def main():
+    global _REAL_STDOUT
+    # keep stdout clean for the one-line contract: everything else this process (or NCCL) prints goes to stderr
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -182,7 +199,8 @@ def main():
     scene = make_scene(args.config)  # same seed on every rank => identical scene
     P = len(scene["pair_views"])
     n_corr = int(scene["m_offset"][1] - scene["m_offset"][0])
-    pgb = B.PoseGraphBuilder(kCoreNumber_=os.cpu_count() or 1, kSimilarityThreshold_=0.0, scene=scene, device=local_rank,
+    pgb = B.PoseGraphBuilder(kCoreNumber_=max(1, (os.cpu_count() or 1) // world),  # ranks share the box's cores
+                              kSimilarityThreshold_=0.0, scene=scene, device=local_rank,
                              wave_size=args.wave, prefetch_fallback=not args.lazy, overlap_fallback=not args.no_overlap, group=group, rank=rank,
                              world_size=world)
     pgb.prepare()
@@ -235,24 +253,51 @@ def main():
     value = P * K / (ms_resident * 1e-3)
     e2e = P * K / (ms_e2e * 1e-3)
 
+    # ---- K1 on full-size waves (HBM roofline probe): every local pair scored against one hypothesis ---------------
+    # In the pipeline K1 only sees the few hundred hypotheses of a round (launch-latency bound); its bandwidth
+    # behaviour is measured here on waves of 8192 pairs x 2000 rows (0.5 GB each, inputs larger than L2).
+    eng = pgb.engine
+    n_local = eng.n_pairs
+    ident = np.tile(np.array([0.0, 0.0, 0.0, 1.0, 1.0, 0.0, 0.0]), (8192, 1))
+    def k1_pass():
+        for s0 in range(0, n_local, 8192):
+            ids = np.arange(s0, min(n_local, s0 + 8192), dtype=np.uint32)
+            eng.run_wave(ids, np.arange(len(ids) + 1, dtype=np.uint32), ident[:len(ids)], flags=B.WAVE_PATH)
+    k1_pass()
+    eng.reset_stats()
+    k1_pass()
+    st_k1 = eng.stats()
+
     # ---- roofline of the dominant kernel (per-stage CUDA-event times from the engine's own stream) -----------
     stages = {"k1_score_hypotheses": st["ms_score"], "k2_fivept_first_solution": st["ms_fivept"],
               "k4_fallback_solve": st["ms_fallback_solve"], "k5_fallback_score": st["ms_fallback_score"],
               "k3_decompose_vote": st["ms_decompose"]}
     dominant = max(stages, key=stages.get)
     hbm_peak, hbm_src = load_peaks()
-    # K5: every scored model evaluates the Sampson residual of all N correspondences: 33 FP64 flops each
+    # K5: every scored model evaluates the Sampson residual of all N correspondences: 33 FP64 flops each (algorithmic)
     k5_flops = st["fallback_models"] * n_corr * 33.0
     k5_t = st["ms_fallback_score"] * 1e-3
-    # K1: 32 B per hypothesis x correspondence evaluation
-    k1_bytes = st["corr_evals"] * 32.0
-    k1_t = st["ms_score"] * 1e-3
+    k5_launches = max(1, K * ((n_local + pgb.fallback_wave - 1) // pgb.fallback_wave) * 8)
     roof_k5 = {"kernel": "k5_fallback_score", "bound": "fp64", "achieved": k5_flops / k5_t / 1e12 if k5_t > 0 else 0.0,
-               "peak": fp64_peak, "unit": "TFLOP/s", "traffic": None,
-               "peak_source": "measured live: DMUL+DADD chains (parity forbids FMA); DFMA peak %.1f TFLOP/s" % fp64_peak_fma}
+               "peak": fp64_peak, "unit": "TFLOP/s",
+               # dram__bytes_read+write per launch from profiles/ (ncu --set full, 1184 pairs x 125 iterations): ~146 MB;
+               # algorithmic bytes per launch = pairs x N x 32 B read once
+               "traffic": NCU_K5_DRAM_BYTES_PER_PAIR_LAUNCH * min(n_local, pgb.fallback_wave),
+               # FP64 rows staged once per CTA + the (72 B FP64 + 48 B FP32) model records of the chunk's iterations
+               "algorithmic_bytes_per_launch": int(min(n_local, pgb.fallback_wave) * (
+                   n_corr * 32 + 120.0 * st["fallback_models"] / max(1, st["fallback_pairs"] * 8))),
+               "launches": k5_launches,
+               "peak_source": "measured live: DMUL+DADD chains (parity forbids FMA); DFMA peak %.1f TFLOP/s; "
+                              "achieved counts 33 algorithmic FP64 flops per model x correspondence evaluation, most of "
+                              "which are certified in FP32 (see DESIGN.md section 3)" % fp64_peak_fma}
     roof_k5["frac"] = roof_k5["achieved"] / fp64_peak if fp64_peak > 0 else None
+    # K1: 32 B per hypothesis x correspondence evaluation, measured on the full-size probe waves above
+    k1_bytes = st_k1["corr_evals"] * 32.0
+    k1_t = st_k1["ms_score"] * 1e-3
     roof_k1 = {"kernel": "k1_score_hypotheses", "bound": "hbm", "achieved": k1_bytes / k1_t / 1e9 if k1_t > 0 else 0.0,
-               "peak": hbm_peak, "unit": "GB/s", "traffic": None, "peak_source": hbm_src + " (MEASURED_PEAKS.json hbm_gbs)"}
+               "peak": hbm_peak, "unit": "GB/s", "traffic": None,
+               "peak_source": hbm_src + " (MEASURED_PEAKS.json hbm_gbs); probe: %d pairs x %d rows per pass, waves of 8192 pairs" % (n_local, n_corr),
+               "gcorr_evals_per_s": st_k1["corr_evals"] / k1_t / 1e9 if k1_t > 0 else 0.0}
     roof_k1["frac"] = roof_k1["achieved"] / hbm_peak
     roofline = dict(roof_k5 if dominant in ("k5_fallback_score", "k4_fallback_solve") else roof_k1)
     roofline["share_of_gpu_time"] = stages[dominant] / max(sum(stages.values()), 1e-9)
@@ -284,7 +329,7 @@ def main():
                                        "(fallback + E->(R,t) vote), %.1f s" % (cpu["pairs"], cpu["seconds"])},
             "clocks": clocks,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
