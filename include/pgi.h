@@ -53,7 +53,7 @@ typedef struct pgi_config {
     uint32_t fallback_max_iters;  /* cv::findEssentialMat USAC default maxIters (1000)                 */
     double threshold_multiplier;  /* 3/2, pose_graph_builder.h:798 and :963                            */
     uint32_t max_wave;            /* capacity hint: pairs per wave (grown on demand)                   */
-    uint32_t flags;               /* reserved, 0                                                       */
+    uint32_t flags;               /* bit 0: background context (lowest stream priority); other bits 0  */
 } pgi_config;
 
 /* Fixed 160-byte verdict record — also the element of the per-wave all-gather. */

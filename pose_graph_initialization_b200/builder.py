@@ -273,7 +273,7 @@ class PoseGraphBuilder:
         self.engine.register_scene(sub, self.thr_px)
         if self.overlap:
             if self.engine_fb is None:
-                self.engine_fb = _engine.Engine(device=self.device, min_inliers=self.min_inliers)
+                self.engine_fb = _engine.Engine(device=self.device, min_inliers=self.min_inliers, background=True)
             self.engine_fb.share_pairs(self.engine)
 
     def engine_stats(self):

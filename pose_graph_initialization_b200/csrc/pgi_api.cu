@@ -68,7 +68,7 @@ struct pgi_ctx {
     uint32_t waveN = 0, waveFlags = 0;
     uint64_t waveMaskRows = 0;
     int nChunks = 0;
-    cudaEvent_t evStart = nullptr, evK1 = nullptr, evK2 = nullptr, evK3 = nullptr, evFbEnd = nullptr;
+    cudaEvent_t evBegin = nullptr, evStart = nullptr, evK1 = nullptr, evK2 = nullptr, evK3 = nullptr, evFbEnd = nullptr;
     cudaEvent_t evChunk[kMaxChunks][2];
     bool fbLaunched = false;
     pgi_stats stats;
@@ -298,7 +298,7 @@ pgi_status submitWave(pgi_ctx *ctx, const Registration &r, uint32_t n, const uin
     memcpy(ctx->h_hypOffset, hypOffset, ((size_t)n + 1) * 4);
     if (nHyp) memcpy(ctx->h_hyp, hyp, (size_t)nHyp * 56);
     cudaStream_t s = ctx->stream;
-    CK(cudaEventRecord(ctx->evStart, s));
+    CK(cudaEventRecord(ctx->evBegin, s));
     CK(cudaMemcpyAsync(ctx->d_pairId, ctx->h_pairId, (size_t)n * 4, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->d_hypOffset, ctx->h_hypOffset, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->d_maskOffset, ctx->h_maskOffset, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, s));
@@ -317,6 +317,7 @@ pgi_status submitWave(pgi_ctx *ctx, const Registration &r, uint32_t n, const uin
     a.thrOverride = thrOverride;
     a.fbSols = ctx->d_fbSols; a.fbSolsF = ctx->d_fbSolsF; a.fbCounts = ctx->d_fbCounts; a.counters = ctx->d_counters;
 
+    CK(cudaEventRecord(ctx->evStart, s));  // kernel-only timing: the wave's small H2D copies are before this event
     k1_score_hypotheses<<<n, kCtaThreads, 0, s>>>(a);
     CK(cudaEventRecord(ctx->evK1, s));
     ctx->stats.launches += 1;
@@ -378,7 +379,7 @@ pgi_status finishWave(pgi_ctx *ctx)
         }
     }
     CK(cudaEventElapsedTime(&ms, ctx->evFbEnd, ctx->evK3)); ctx->stats.ms_decompose += ms;
-    CK(cudaEventElapsedTime(&ms, ctx->evStart, ctx->evK3)); ctx->stats.ms_total += ms;
+    CK(cudaEventElapsedTime(&ms, ctx->evBegin, ctx->evK3)); ctx->stats.ms_total += ms;
     ctx->stats.corr_evals += ctx->h_counters[0];
     ctx->stats.fallback_pairs += ctx->h_counters[1];
     ctx->stats.fallback_models += ctx->h_counters[2];
@@ -423,8 +424,15 @@ pgi_status pgi_create(const pgi_config *cfg, pgi_ctx **out)
     memset(&ctx->stats, 0, sizeof ctx->stats);
     auto fail = [&](pgi_status s) { pgi_destroy(ctx); return s; };
     if (cudaSetDevice(cfg->device) != cudaSuccess) return fail(PGI_ERR_CUDA);
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(PGI_ERR_CUDA);
-    cudaEvent_t *evs[] = {&ctx->evStart, &ctx->evK1, &ctx->evK2, &ctx->evK3, &ctx->evFbEnd};
+    {
+        // flags bit 0: background context (lowest stream priority) — used for the hypothesis-independent fallback
+        // prefetch so that the latency-critical wave kernels of the foreground context get SM slots first
+        int prioLow = 0, prioHigh = 0;
+        cudaDeviceGetStreamPriorityRange(&prioLow, &prioHigh);
+        const int prio = (ctx->cfg.flags & 1u) ? prioLow : prioHigh;
+        if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio) != cudaSuccess) return fail(PGI_ERR_CUDA);
+    }
+    cudaEvent_t *evs[] = {&ctx->evBegin, &ctx->evStart, &ctx->evK1, &ctx->evK2, &ctx->evK3, &ctx->evFbEnd};
     for (auto e : evs)
         if (cudaEventCreate(e) != cudaSuccess) return fail(PGI_ERR_CUDA);
     for (int c = 0; c < kMaxChunks; c++)
@@ -451,7 +459,7 @@ pgi_status pgi_destroy(pgi_ctx *ctx)
     cudaFree(ctx->d_verdicts); cudaFree(ctx->d_fbSols); cudaFree(ctx->d_fbSolsF); cudaFree(ctx->d_counters);
     cudaFreeHost(ctx->h_pairId); cudaFreeHost(ctx->h_hypOffset); cudaFreeHost(ctx->h_hyp);
     cudaFreeHost(ctx->h_maskOffset); cudaFreeHost(ctx->h_verdicts); cudaFreeHost(ctx->h_counters);
-    cudaEvent_t evs[] = {ctx->evStart, ctx->evK1, ctx->evK2, ctx->evK3, ctx->evFbEnd};
+    cudaEvent_t evs[] = {ctx->evBegin, ctx->evStart, ctx->evK1, ctx->evK2, ctx->evK3, ctx->evFbEnd};
     for (auto e : evs)
         if (e) cudaEventDestroy(e);
     for (int c = 0; c < kMaxChunks; c++)

@@ -19,6 +19,7 @@
 namespace pgi {
 
 constexpr int kCtaThreads = 256;
+constexpr int kK1Rows = 4;            // rows per thread and tile in K1 (8 x 32 B of loads in flight per thread)
 constexpr int kFbChunk = 125;         // fallback iterations solved per K4 launch
 constexpr int kLoRounds = 4;
 constexpr int kLoMinInliers = 9;
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(256) k0_build_correspondences(
 // un-squared (getInliers, GT:164) thresholds with warp ballots; the last passing hypothesis' inlier
 // bits are kept for the sampler of K2.  HBM-bound: 32 B / correspondence, read once per hypothesis.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kCtaThreads) k1_score_hypotheses(WaveArgs a)
+__global__ void __launch_bounds__(kCtaThreads, 3) k1_score_hypotheses(WaveArgs a)
 {
     const uint32_t w = blockIdx.x;
     if (w >= a.n) return;
@@ -138,7 +139,6 @@ __global__ void __launch_bounds__(kCtaThreads) k1_score_hypotheses(WaveArgs a)
     uint8_t *mask = (a.flags & PGI_WAVE_MASKS) ? a.masks + a.maskOffset[w] : nullptr;
     const bool noTest = (a.flags & PGI_WAVE_NO_TEST) != 0;
 
-    __shared__ double sE[9];
     __shared__ uint32_t sCnt[2][kCtaThreads / 32];
     __shared__ uint32_t sDecision, sValidSel;
     if (threadIdx.x == 0) sValidSel = 0;
@@ -150,30 +150,66 @@ __global__ void __launch_bounds__(kCtaThreads) k1_score_hypotheses(WaveArgs a)
 
     uint32_t flags = 0, testCount = 0, pathInliers = 0;
     for (uint32_t h = h0; h < h1; ++h) {
-        __syncthreads();
-        if (threadIdx.x == 0) essentialFromPose(a.hyp + 7 * (size_t)h, sE);
-        __syncthreads();
+        __syncthreads();  // sValidSel of the previous hypothesis is final
+        // every thread derives E = [t]x R itself (identical operations, broadcast loads): no serial section
         double E[9];
+        {
+            double qt[7];
 #pragma unroll
-        for (int k = 0; k < 9; k++) E[k] = sE[k];
+            for (int k = 0; k < 7; k++) qt[k] = a.hyp[7 * (size_t)h + k];
+            essentialFromPose(qt, E);
+        }
         const uint32_t cur = 1u - sValidSel;
         uint32_t *bits = bitsBase + (size_t)cur * a.bitsStride;
         uint32_t cTest = 0, cInl = 0;
-        const uint32_t nRound = (N + 31u) & ~31u;
-        for (uint32_t i = threadIdx.x; i < nRound; i += blockDim.x) {
-            bool t = false, in = false;
-            if (i < N) {
-                const double4 c = rows[i];
-                const double s = sampsonSq(c.x, c.y, c.z, c.w, E);
-                t = s < thrTsq;  // GT:214
-                in = s < thrT;   // GT:164 (un-squared threshold, reproduced)
+        // Tiles of kK1Rows rows per thread: all loads of a tile are issued before any arithmetic (8 x 32 B in flight
+        // per thread), then the residuals are classified.  The FP64 division of graph_traversal.h:114 is only
+        // executed when the comparison is not already decided by  r^2  vs  thr * denom  with a 2^-50 guard band
+        // (fl(r2/den) < T  is implied by  r2 < T den (1 - 2^-50)  and excluded by  r2 > T den (1 + 2^-50)), so the
+        // result is bit-identical to dividing every time.
+        const uint32_t tileRows = kK1Rows * kCtaThreads;
+        for (uint32_t base = 0; base < N; base += tileRows) {
+            double4 c[kK1Rows];
+#pragma unroll
+            for (int u = 0; u < kK1Rows; u++) {
+                const uint32_t i = base + u * kCtaThreads + threadIdx.x;
+                c[u] = i < N ? rows[i] : make_double4(0.0, 0.0, 0.0, 0.0);
             }
-            const uint32_t bt = __ballot_sync(0xffffffffu, t);
-            const uint32_t bi = __ballot_sync(0xffffffffu, in);
-            if (lane == 0) {
-                cTest += __popc(bt);
-                cInl += __popc(bi);
-                bits[i >> 5] = bi;
+#pragma unroll
+            for (int u = 0; u < kK1Rows; u++) {
+                const uint32_t i = base + u * kCtaThreads + threadIdx.x;
+                if (base + u * kCtaThreads >= N) break;  // warp-uniform: whole row group past the end
+                bool t = false, in = false;
+                if (i < N) {
+                    const double x1 = c[u].x, y1 = c[u].y, x2 = c[u].z, y2 = c[u].w;
+                    const double rxc = E[0] * x2 + E[3] * y2 + E[6];
+                    const double ryc = E[1] * x2 + E[4] * y2 + E[7];
+                    const double rwc = E[2] * x2 + E[5] * y2 + E[8];
+                    const double r = (x1 * rxc + y1 * ryc + rwc);
+                    const double rx = E[0] * x1 + E[1] * y1 + E[2];
+                    const double ry = E[3] * x1 + E[4] * y1 + E[5];
+                    const double r2 = r * r;
+                    const double den = rxc * rxc + ryc * ryc + rx * rx + ry * ry;
+                    const double q1 = thrTsq * den, q2 = thrT * den;
+                    const double lo = 1.0 - 8.8817841970012523e-16, hi = 1.0 + 8.8817841970012523e-16;  // 1 -+ 2^-50
+                    const bool sure1 = q1 > 1e-290 && (r2 < q1 * lo || r2 > q1 * hi);
+                    const bool sure2 = q2 > 1e-290 && (r2 < q2 * lo || r2 > q2 * hi);
+                    if (sure1 && sure2) {
+                        t = r2 < q1;
+                        in = r2 < q2;
+                    } else {
+                        const double sres = r2 / den;  // the reference's expression, evaluated only near a boundary
+                        t = sres < thrTsq;             // GT:214
+                        in = sres < thrT;              // GT:164 (un-squared threshold, reproduced)
+                    }
+                }
+                const uint32_t bt = __ballot_sync(0xffffffffu, t);
+                const uint32_t bi = __ballot_sync(0xffffffffu, in);
+                if (lane == 0) {
+                    cTest += __popc(bt);
+                    cInl += __popc(bi);
+                    bits[i >> 5] = bi;
+                }
             }
         }
         if (lane == 0) { sCnt[0][warp] = cTest; sCnt[1][warp] = cInl; }

@@ -94,11 +94,11 @@ class PgiError(RuntimeError):
 class Engine:
     """One context per (process, GPU)."""
 
-    def __init__(self, device=0, min_inliers=20, test_min_inliers=5, fallback_max_iters=1000, max_wave=4096):
+    def __init__(self, device=0, min_inliers=20, test_min_inliers=5, fallback_max_iters=1000, max_wave=4096, background=False):
         self.lib = load_library()
         if self.lib.pgi_device_count() <= 0:
             raise PgiError("no usable sm_100 CUDA device: the hypothesis-verification engine has no CPU path")
-        cfg = PgiConfig(device, min_inliers, test_min_inliers, fallback_max_iters, 1.5, max_wave, 0)
+        cfg = PgiConfig(device, min_inliers, test_min_inliers, fallback_max_iters, 1.5, max_wave, 1 if background else 0)
         h = C.c_void_p()
         st = self.lib.pgi_create(C.byref(cfg), C.byref(h))
         if st != PGI_OK:
