@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(64, 6) k4_fallback_solve(WaveArgs a, int chunk
 // oracle/pgo_fallback.hpp): terms are produced by IEEE FP64 operations, converted to integers once and
 // added with integer arithmetic, so warps/CTAs may reduce in any order (shuffles, shared-memory atomics).
 // ---------------------------------------------------------------------------------------------
-constexpr int kBatch = 8;                     // fallback iterations scored between two decision points of K5
+constexpr int kBatch = 16;                    // fallback iterations scored between two decision points of K5
 constexpr double kCostOne = 4294967296.0;     // fixed-point MSAC cost of an outlier (2^32)
 constexpr double kLsScale = 1099511627776.0;  // 2^40: fixed-point scale of the normal-equation products
 
@@ -437,9 +437,11 @@ __device__ __forceinline__ void exactTerm(const double4 *rows, uint32_t i, const
 // bit in a per-thread mask.  Afterwards each warp compacts its masks into a shared-memory queue (one prefix scan)
 // and the exact FP64 path runs DENSELY, 32 queued correspondences at a time, so the FP64 pipe only sees the few
 // percent of evaluations that can matter.  Returns the warp's partial (cost, inliers) per model in lane 0.
-__device__ __forceinline__ void exactQueue(const double4 *rows, const double *Eg, unsigned long long mask, uint16_t *queue,
-                                           double thrSq, double truncSq, double invT, unsigned long long &cost, uint32_t &inl)
+__device__ __forceinline__ void exactQueue(const double4 *rows, const double *Eg, unsigned long long mask, uint32_t base,
+                                           uint16_t *queue, double thrSq, double truncSq, double invT,
+                                           unsigned long long &cost, uint32_t &inl)
 {
+    // bit j of `mask` = correspondence  base + lane + 32 j  of this lane is uncertain
     const int lane = threadIdx.x & 31;
     const uint32_t mine = (uint32_t)__popcll(mask);
     uint32_t incl = mine;
@@ -454,20 +456,23 @@ __device__ __forceinline__ void exactQueue(const double4 *rows, const double *Eg
     while (mask) {
         const int j = __ffsll((long long)mask) - 1;
         mask &= mask - 1;
-        queue[pos++] = (uint16_t)(threadIdx.x + j * kCtaThreads);
+        queue[pos++] = (uint16_t)(base + lane + 32 * j);
     }
     __syncwarp();
-    for (uint32_t base = 0; base < total; base += 32)
-        if (base + lane < total) exactTerm(rows, queue[base + lane], Eg, thrSq, truncSq, invT, cost, inl);
+    for (uint32_t b0 = 0; b0 < total; b0 += 32)
+        if (b0 + lane < total) exactTerm(rows, queue[b0 + lane], Eg, thrSq, truncSq, invT, cost, inl);
     __syncwarp();
 }
 
 template <bool USE_F32>
 __device__ __forceinline__ void scoreModelsWarp(const double4 *rows, const float4 *pts, uint32_t N, const double *Eg0,
                                                 const double *Eg1 /*null: one model*/, const float4 *Ef /*3 float4 per model*/,
-                                                double thrSq, double truncSq, double invT, float rOut, uint16_t *queue,
+                                                double thrSq, double truncSq, double invT, float rOut, uint16_t *queue /*2048*/,
                                                 unsigned long long costOut[2], uint32_t inlOut[2])
 {
+    // ONE warp scores the model(s) over all N correspondences (lane l: points l, l + 32, ...), in blocks of 2048
+    // points so that a lane's uncertainty mask fits 64 bits.  No cross-warp reduction is needed.
+    const uint32_t lane = threadIdx.x & 31;
     unsigned long long cost0 = 0, cost1 = 0;
     uint32_t inl0 = 0, inl1 = 0;
     const bool two = Eg1 != nullptr;
@@ -475,32 +480,35 @@ __device__ __forceinline__ void scoreModelsWarp(const double4 *rows, const float
         const float4 a0 = Ef[0], a1 = Ef[1], a2 = Ef[2];  // e0..e8 of model 0
         float4 b0 = a0, b1 = a1, b2 = a2;
         if (two) { b0 = Ef[3]; b1 = Ef[4]; b2 = Ef[5]; }
-        unsigned long long m0 = 0, m1 = 0;
-        uint32_t j = 0;
+        for (uint32_t blk = 0; blk < N; blk += 2048) {
+            unsigned long long m0 = 0, m1 = 0;
+            const uint32_t end = N - blk < 2048 ? N - blk : 2048;  // points in this block
+            uint32_t j = 0;
 #pragma unroll 4
-        for (uint32_t i = threadIdx.x; i < N; i += kCtaThreads, ++j) {
-            const float4 p = pts[i];
-            // model 0: E = [a0.x a0.y a0.z; a0.w a1.x a1.y; a1.z a1.w a2.x]
-            const float rxc0 = fmaf(a0.x, p.z, fmaf(a0.w, p.w, a1.z));
-            const float ryc0 = fmaf(a0.y, p.z, fmaf(a1.x, p.w, a1.w));
-            const float rwc0 = fmaf(a0.z, p.z, fmaf(a1.y, p.w, a2.x));
-            const float r0 = fmaf(p.x, rxc0, fmaf(p.y, ryc0, rwc0));
-            const float rxc1 = fmaf(b0.x, p.z, fmaf(b0.w, p.w, b1.z));
-            const float ryc1 = fmaf(b0.y, p.z, fmaf(b1.x, p.w, b1.w));
-            const float rwc1 = fmaf(b0.z, p.z, fmaf(b1.y, p.w, b2.x));
-            const float r1 = fmaf(p.x, rxc1, fmaf(p.y, ryc1, rwc1));
-            m0 |= (unsigned long long)(!(fabsf(r0) > rOut)) << j;  // NaN stays uncertain
-            m1 |= (unsigned long long)(!(fabsf(r1) > rOut)) << j;
-        }
-        const uint32_t nPts = N > threadIdx.x ? (N - threadIdx.x + kCtaThreads - 1) / kCtaThreads : 0u;
-        cost0 = (unsigned long long)(nPts - (uint32_t)__popcll(m0)) << 32;
-        exactQueue(rows, Eg0, m0, queue, thrSq, truncSq, invT, cost0, inl0);
-        if (two) {
-            cost1 = (unsigned long long)(nPts - (uint32_t)__popcll(m1)) << 32;
-            exactQueue(rows, Eg1, m1, queue, thrSq, truncSq, invT, cost1, inl1);
+            for (uint32_t o = lane; o < end; o += 32, ++j) {
+                const float4 p = pts[blk + o];
+                // model 0: E = [a0.x a0.y a0.z; a0.w a1.x a1.y; a1.z a1.w a2.x]
+                const float rxc0 = fmaf(a0.x, p.z, fmaf(a0.w, p.w, a1.z));
+                const float ryc0 = fmaf(a0.y, p.z, fmaf(a1.x, p.w, a1.w));
+                const float rwc0 = fmaf(a0.z, p.z, fmaf(a1.y, p.w, a2.x));
+                const float r0 = fmaf(p.x, rxc0, fmaf(p.y, ryc0, rwc0));
+                const float rxc1 = fmaf(b0.x, p.z, fmaf(b0.w, p.w, b1.z));
+                const float ryc1 = fmaf(b0.y, p.z, fmaf(b1.x, p.w, b1.w));
+                const float rwc1 = fmaf(b0.z, p.z, fmaf(b1.y, p.w, b2.x));
+                const float r1 = fmaf(p.x, rxc1, fmaf(p.y, ryc1, rwc1));
+                m0 |= (unsigned long long)(!(fabsf(r0) > rOut)) << j;  // NaN stays uncertain
+                m1 |= (unsigned long long)(!(fabsf(r1) > rOut)) << j;
+            }
+            const uint32_t nPts = end > lane ? (end - lane + 31) / 32 : 0u;
+            cost0 += (unsigned long long)(nPts - (uint32_t)__popcll(m0)) << 32;
+            exactQueue(rows, Eg0, m0, blk, queue, thrSq, truncSq, invT, cost0, inl0);
+            if (two) {
+                cost1 += (unsigned long long)(nPts - (uint32_t)__popcll(m1)) << 32;
+                exactQueue(rows, Eg1, m1, blk, queue, thrSq, truncSq, invT, cost1, inl1);
+            }
         }
     } else {
-        for (uint32_t i = threadIdx.x; i < N; i += kCtaThreads) {
+        for (uint32_t i = lane; i < N; i += 32) {
             exactTerm(rows, i, Eg0, thrSq, truncSq, invT, cost0, inl0);
             if (two) exactTerm(rows, i, Eg1, thrSq, truncSq, invT, cost1, inl1);
         }
@@ -720,23 +728,25 @@ __device__ __forceinline__ void k5Body(const WaveArgs &a, int chunk, int lastChu
             // ---- phase 1: score every model of the next kBatch iterations (pure functions of the models) ----------
             int nb = itEnd - it < kBatch ? itEnd - it : kBatch;
             nb = sMaxIters - it < nb ? sMaxIters - it : nb;
+            int pass = 0;  // running index of (iteration, model pair) passes of this batch; warp = pass mod 8
             for (int bI = 0; bI < nb; bI++) {
                 const int j = it + bI - chunk * kFbChunk;
                 const int ns = a.fbCounts[(size_t)w * kFbChunk + j];
                 const double *sols = a.fbSols + ((size_t)w * kFbChunk + j) * 90;
                 const float4 *solsF = a.fbSolsF + ((size_t)w * kFbChunk + j) * 30;
-                for (int q = 0; q < ns; q += 2) {
+                for (int q = 0; q < ns; q += 2, ++pass) {
+                    if ((pass & 7) != warp) continue;
                     unsigned long long c[2];
                     uint32_t n[2];
                     const bool two = q + 1 < ns;
                     scoreModelsWarp<USE_F32>(rows, sPts, N, sols + q * 9, two ? sols + (q + 1) * 9 : nullptr, solsF + q * 3, thrSq,
                                              truncSq, invT, fc.rOut, sQueue, c, n);
                     if (lane == 0) {
-                        atomicAdd(&sCost[bI][q], c[0]);
-                        atomicAdd(&sInl[bI][q], n[0]);
+                        sCost[bI][q] = c[0];
+                        sInl[bI][q] = n[0];
                         if (two) {
-                            atomicAdd(&sCost[bI][q + 1], c[1]);
-                            atomicAdd(&sInl[bI][q + 1], n[1]);
+                            sCost[bI][q + 1] = c[1];
+                            sInl[bI][q + 1] = n[1];
                         }
                     }
                 }
@@ -781,12 +791,19 @@ __device__ __forceinline__ void k5Body(const WaveArgs &a, int chunk, int lastChu
                         sLoInl = 0;
                     }
                     __syncthreads();
-                    unsigned long long c[2];
-                    uint32_t n[2];
-                    scoreModelsWarp<USE_F32>(rows, sPts, N, sEls, nullptr, sElsF, thrSq, truncSq, invT, fc.rOut, sQueue, c, n);
-                    if (lane == 0) {
-                        atomicAdd(&sLoCost, c[0]);
-                        atomicAdd(&sLoInl, n[0]);
+                    // the refit model is scored by the 8 warps on disjoint 1/8 slices of the points (fixed-point sums)
+                    {
+                        const uint32_t per = ((N + 7) / 8 + 31) & ~31u;
+                        const uint32_t lo = warp * per < N ? warp * per : N;
+                        const uint32_t hi = lo + per < N ? lo + per : N;
+                        unsigned long long c[2];
+                        uint32_t n[2];
+                        scoreModelsWarp<USE_F32>(rows + lo, sPts + lo, hi - lo, sEls, nullptr, sElsF, thrSq, truncSq, invT, fc.rOut,
+                                                 sQueue, c, n);
+                        if (lane == 0) {
+                            atomicAdd(&sLoCost, c[0]);
+                            atomicAdd(&sLoInl, n[0]);
+                        }
                     }
                     __syncthreads();
                     if (threadIdx.x == 0) {
@@ -868,8 +885,8 @@ __global__ void __launch_bounds__(kCtaThreads, 3) k5_fallback_score(WaveArgs a, 
     if (!(a.state[w].flags & ST_NEED_FB)) return;
     const uint32_t pid = a.pairId[w];
     const uint32_t N = (uint32_t)(a.offset[pid + 1] - a.offset[pid]);
-    // dynamic shared memory: smemPts float4 points, then 8 per-warp queues of 32 * ceil(smemPts / 256) uint16 indices
-    const uint32_t queueStride = 32u * ((smemPts + kCtaThreads - 1) / kCtaThreads);
+    // dynamic shared memory: smemPts float4 points, then 8 per-warp queues of min(smemPts, 2048) uint16 indices
+    const uint32_t queueStride = smemPts < 2048u ? ((smemPts + 31u) & ~31u) : 2048u;
     uint16_t *sQueueAll = reinterpret_cast<uint16_t *>(sPts + smemPts);
     if (N <= smemPts)
         k5Body<true>(a, chunk, lastChunk, w, sPts, sQueueAll, queueStride);
