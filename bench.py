@@ -166,6 +166,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--config", default="cfg2_300v")
     ap.add_argument("--wave", type=int, default=1024)
+    ap.add_argument("--window", type=int, default=0, help="host re-search window (0 = library default)")
     ap.add_argument("--no-overlap", action="store_true", help="prefetch the fallback before the waves instead of concurrently")
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the cpu_baseline sample (0 = 256 x cores, ~10-15 s)")
     ap.add_argument("--lazy", action="store_true", help="run the fallback lazily inside the waves instead of prefetching it")
@@ -197,11 +198,17 @@ def main():
         torch.cuda.synchronize()
 
     scene = make_scene(args.config)  # same seed on every rank => identical scene
+    # the step's host inputs live in PINNED memory (the e2e leg copies them host->device every step)
+    for key in ("matches", "kp", "sim", "pair_views", "m_offset", "kp_offset", "focal", "size"):
+        src = np.ascontiguousarray(scene[key])
+        pinned = torch.empty(src.nbytes, dtype=torch.uint8, pin_memory=True).numpy().view(src.dtype).reshape(src.shape)
+        pinned[...] = src
+        scene[key] = pinned
     P = len(scene["pair_views"])
     n_corr = int(scene["m_offset"][1] - scene["m_offset"][0])
     pgb = B.PoseGraphBuilder(kCoreNumber_=max(1, (os.cpu_count() or 1) // world),  # ranks share the box's cores
                               kSimilarityThreshold_=0.0, scene=scene, device=local_rank,
-                             wave_size=args.wave, prefetch_fallback=not args.lazy, overlap_fallback=not args.no_overlap, group=group, rank=rank,
+                             wave_size=args.wave, prefetch_fallback=not args.lazy, overlap_fallback=not args.no_overlap, research_window=args.window, group=group, rank=rank,
                              world_size=world)
     pgb.prepare()
     fp64_peak = pgb.engine.fp64_peak(fused=False)

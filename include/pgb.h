@@ -41,7 +41,7 @@ typedef struct pgb_config {
     int32_t use_path_finding;            /* cpp_example.cpp:36  (true) */
     int32_t host_threads;                /* threads for the speculative A* (core_number analogue) */
     int32_t lazy_fallback;               /* 1: waves carry PATH|FALLBACK; 0: fallback verdicts are prefetched */
-    int32_t reserved;
+    int32_t reserved;                    /* re-search window behind the first stale position (0 = unlimited) */
 } pgb_config;
 
 typedef struct pgb_item {

@@ -83,10 +83,10 @@ class HostBuilder:
 
     def __init__(self, scene, similarity_threshold=0.5, minimum_inlier_number=20, minimum_point_number=50,
                  maximum_search_depth=5, traversal_heuristics_weight=0.8, use_path_finding=True, host_threads=0,
-                 lazy_fallback=False):
+                 lazy_fallback=False, research_window=0):
         self.lib = _host_lib()
         cfg = PgbConfig(similarity_threshold, minimum_inlier_number, minimum_point_number, maximum_search_depth,
-                        traversal_heuristics_weight, 1 if use_path_finding else 0, host_threads, 1 if lazy_fallback else 0, 0)
+                        traversal_heuristics_weight, 1 if use_path_finding else 0, host_threads, 1 if lazy_fallback else 0, research_window)
         sim = np.ascontiguousarray(scene["sim"], dtype=np.float64)
         pv = np.ascontiguousarray(scene["pair_views"], dtype=np.uint32)
         mo = np.ascontiguousarray(scene["m_offset"], dtype=np.uint64)
@@ -234,8 +234,8 @@ class PoseGraphBuilder:
                  kTraversalHeuristicsWeight_=0.8, kSimilarityThreshold_=0.5, kInlierOutlierThreshold_=0.4,
                  kImagePath_="", kWorkspacePath_="", kSimilarityGraphPath_="", kFocalLengthPath_="",
                  kUsePathFinding_=True, kUseGPU_=True, kUseEpipolarHashing_=False, *, scene=None, device=0,
-                 wave_size=1024, prefetch_fallback=True, fallback_wave=2048, overlap_fallback=True, group=None, rank=0,
-                 world_size=1):
+                 wave_size=1024, prefetch_fallback=True, fallback_wave=2048, overlap_fallback=True, research_window=0,
+                 group=None, rank=0, world_size=1):
         if not kUseGPU_:
             raise ValueError("the B200 path has no CPU implementation (kUseGPU_ must be true)")
         if kUseEpipolarHashing_:
@@ -246,7 +246,7 @@ class PoseGraphBuilder:
         self.cfg = dict(similarity_threshold=kSimilarityThreshold_, minimum_inlier_number=kMinimumInlierNumber_,
                         minimum_point_number=kMinimumPointNumber_, maximum_search_depth=kMaximumSearchDepth_,
                         traversal_heuristics_weight=kTraversalHeuristicsWeight_, use_path_finding=kUsePathFinding_,
-                        host_threads=kCoreNumber_)
+                        host_threads=kCoreNumber_, research_window=research_window)
         self.thr_px = kInlierOutlierThreshold_
         self.min_inliers = kMinimumInlierNumber_
         self.device = device

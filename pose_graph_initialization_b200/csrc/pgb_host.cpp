@@ -575,11 +575,13 @@ void searchPosition(pgb_builder *b, uint32_t k, AStarScratch &S)
     it.searched = true;
 }
 
-void searchStale(pgb_builder *b)
+// Search the stale positions below `limit` (pgb_config.reserved can restrict the re-search to a window behind the
+// first stale position; unlimited by default).
+void searchStale(pgb_builder *b, uint32_t limit)
 {
     const double t0 = nowSec();
     std::vector<uint32_t> todo;
-    for (uint32_t k = 0; k < b->wave.size(); k++)
+    for (uint32_t k = 0; k < b->wave.size() && k < limit; k++)
         if (!b->wave[k].searched) todo.push_back(k);
     if (b->cfg.host_threads <= 1 || todo.size() < 4) {
         for (uint32_t k : todo) searchPosition(b, k, b->scratch[0]);
@@ -606,7 +608,7 @@ uint32_t resolveVerdicts(pgb_builder *b)
     for (Item &it : b->wave) {
         it.needGpu = false;
         it.finalV = it.pathV = nullptr;
-        if (it.staticSkip) continue;
+        if (it.staticSkip || !it.searched) continue;  // unsearched positions wait for the window to reach them
         if (it.hasHyp) {
             auto pc = b->pathCache.find(makeKey(it.pairId, it.hyp));
             if (pc == b->pathCache.end()) { it.needGpu = true; ++need; continue; }
@@ -676,14 +678,21 @@ uint32_t advanceWave(pgb_builder *b)
 {
     const uint32_t n = (uint32_t)b->wave.size();
     for (;;) {
-        searchStale(b);
+        uint32_t firstStale = n;
+        for (uint32_t k = 0; k < n; k++)
+            if (!b->wave[k].searched) { firstStale = k; break; }
+        // optional re-search window behind the first stale position (0 = unlimited: measured best on cfg2, the
+        // re-search cascade is intrinsic rather than wasted look-ahead)
+        const uint32_t window = b->cfg.reserved > 0 ? (uint32_t)b->cfg.reserved : n;
+        const uint32_t limit = firstStale + window < n ? firstStale + window : n;
+        searchStale(b, limit);
         if (resolveVerdicts(b) > 0) return 0;  // engine round trip needed; the wave stays open
         // actual outcomes vs. the predictions the overlay was built from
         std::fill(b->minChangedPos.begin(), b->minChangedPos.end(), UINT32_MAX);
         uint32_t firstChanged = UINT32_MAX;
         for (uint32_t k = 0; k < n; k++) {
             Item &it = b->wave[k];
-            if (it.staticSkip) continue;
+            if (it.staticSkip || !it.searched) continue;
             const Outcome act = outcomeOf(it.finalV);
             if (!act.sameEdge(it.pred)) {
                 it.pred = act;
@@ -692,7 +701,13 @@ uint32_t advanceWave(pgb_builder *b)
                 b->minChangedPos[it.dst] = std::min(b->minChangedPos[it.dst], k);
             }
         }
-        if (firstChanged == UINT32_MAX) break;  // fixed point: every search saw exactly the sequential graph
+        if (firstChanged == UINT32_MAX) {
+            bool allSearched = true;
+            for (uint32_t k = limit; k < n && allSearched; k++) allSearched = b->wave[k].searched;
+            if (allSearched) break;  // fixed point: every search saw exactly the sequential graph
+            ++b->rounds;
+            continue;                // nothing changed inside the window: move it forward
+        }
         ++b->rounds;
         for (uint32_t m = firstChanged + 1; m < n; m++) {
             Item &it = b->wave[m];
@@ -845,7 +860,7 @@ uint32_t pgb_next_wave(pgb_builder *b, uint32_t max_items, pgb_item *items)
     b->ctr.waves++;
     b->ctr.items_speculated += b->wave.size();
     rebuildOverlay(b);
-    searchStale(b);
+    searchStale(b, (uint32_t)b->wave.size());
     resolveVerdicts(b);
     return emitItems(b, items);
 }
