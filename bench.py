@@ -329,7 +329,8 @@ def main():
                                     "fallback_models": st["fallback_models"] * n_corr / (ms_resident * 1e-3) / 1e9},
             "roofline": roofline, "roofline_k1_scoring": roof_k1, "roofline_k5_fallback": roof_k5,
             "gpu_stage_ms_per_step": {k: v / K for k, v in stages.items()},
-            "host_s_per_step": {k: timing.get(k) for k in ("prefetch_s", "waves_s", "total_s")},
+            "host_s_per_step": {k: timing.get(k) for k in ("prefetch_s", "waves_s", "total_s", "engine_s", "exchange_s", "host_s",
+                                                            "wait_prefetch_s", "engine_rounds", "exchanges")},
             "host_counters": counters, "edges": int(n_edges), "wall_s_resident": wall,
             "cpu_baseline": {"value": cpu["pairs_per_s"], "unit": "pairs/s", "cores": cpu["cores"], "kind": "port",
                              "sample": "%d evenly spaced pairs of the same scene through the oracle's estimatePose "

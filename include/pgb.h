@@ -70,6 +70,16 @@ typedef struct pgb_log {  /* one record per pair popped from the queue, in proce
     double E[9], q[4], t[3], score;
 } pgb_log;
 
+/* Exchange record of one wave position (multi-rank): filled by the position's owner, zero elsewhere, merged by a
+ * byte-wise SUM all-reduce. */
+typedef struct pgb_record {
+    uint8_t valid, has_hyp, has_path_verdict, final_is_path;
+    uint32_t touched;
+    pgi_verdict v;   /* the owner's verdict for (pair, hypothesis) if has_path_verdict */
+} pgb_record;
+
+enum { PGB_WAVE_DONE = 0, PGB_WAVE_NEED_GPU = 1, PGB_WAVE_NEED_EXCHANGE = 2 };
+
 typedef struct pgb_counters {
     uint64_t pairs_popped, committed, path_accepted, fallback_accepted, rejected, skipped;
     uint64_t waves, items_speculated, items_requeued, astar_runs, astar_reruns, verdict_cache_hits;
@@ -103,6 +113,16 @@ uint32_t pgb_next_wave(pgb_builder *b, uint32_t max_items, pgb_item *items);
 /* verdicts: one per item with need_gpu != 0, in item order.  Returns the number of items committed
  * (accepted, rejected or skipped); the rest were re-queued. */
 uint32_t pgb_commit_wave(pgb_builder *b, const pgi_verdict *verdicts, uint32_t n_verdicts);
+
+/* Multi-rank (SPMD, one process per GPU): rank r searches and verifies only the positions whose pair id lies in
+ * [bounds[r], bounds[r+1]); after each round the ranks exchange pgb_record arrays (pgb_export_records -> byte-wise
+ * SUM all-reduce -> pgb_import_records) so that every rank applies the same outcomes and commits the same graph.
+ * pgb_wave_status tells the driver what the open wave waits for. */
+int32_t pgb_set_partition(pgb_builder *b, int32_t rank, int32_t world, const uint64_t *bounds);
+int32_t pgb_wave_status(pgb_builder *b);
+uint32_t pgb_wave_size(pgb_builder *b);
+void pgb_export_records(pgb_builder *b, pgb_record *out);
+uint32_t pgb_import_records(pgb_builder *b, const pgb_record *in);
 
 uint64_t pgb_edge_count(pgb_builder *b);
 void pgb_copy_edges(pgb_builder *b, pgb_edge *out);

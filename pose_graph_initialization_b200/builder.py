@@ -50,8 +50,13 @@ class PgbCounters(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+RECORD_DTYPE = np.dtype([("valid", np.uint8), ("has_hyp", np.uint8), ("has_path_verdict", np.uint8), ("final_is_path", np.uint8),
+                         ("touched", np.uint32), ("v", VERDICT_DTYPE)], align=True)
+WAVE_DONE, WAVE_NEED_GPU, WAVE_NEED_EXCHANGE = 0, 1, 2
+
 PGB_EXPORTS = ["pgb_create", "pgb_destroy", "pgb_remaining", "pgb_set_fallback_verdicts", "pgb_set_fallback_verdicts_some",
-               "pgb_queue_size", "pgb_queue_pairs", "pgb_next_wave",
+               "pgb_queue_size", "pgb_queue_pairs", "pgb_set_partition", "pgb_wave_status", "pgb_wave_size",
+               "pgb_export_records", "pgb_import_records", "pgb_next_wave",
                "pgb_commit_wave", "pgb_edge_count", "pgb_copy_edges", "pgb_log_count", "pgb_copy_log", "pgb_get_counters",
                "pgb_astar"]
 
@@ -68,6 +73,10 @@ def _host_lib():
         lib.pgb_log_count.restype = C.c_uint64
         lib.pgb_next_wave.restype = C.c_uint32
         lib.pgb_commit_wave.restype = C.c_uint32
+        lib.pgb_import_records.restype = C.c_uint32
+        lib.pgb_wave_size.restype = C.c_uint32
+        lib.pgb_wave_status.restype = C.c_int32
+        lib.pgb_set_partition.restype = C.c_int32
         for name in PGB_EXPORTS[1:]:
             getattr(lib, name).argtypes = None
         lib._pgb_ready = True
@@ -139,6 +148,24 @@ class HostBuilder:
         verdicts = np.ascontiguousarray(verdicts, dtype=VERDICT_DTYPE)
         return int(self.lib.pgb_commit_wave(self.h, _ptr(verdicts), C.c_uint32(len(verdicts))))
 
+    def set_partition(self, rank, world, bounds):
+        bounds = np.ascontiguousarray(bounds, dtype=np.uint64)
+        if self.lib.pgb_set_partition(self.h, C.c_int32(rank), C.c_int32(world), _ptr(bounds)) != 0:
+            raise RuntimeError("pgb_set_partition failed")
+
+    def wave_status(self):
+        return int(self.lib.pgb_wave_status(self.h))
+
+    def export_records(self):
+        out = np.zeros(int(self.lib.pgb_wave_size(self.h)), dtype=RECORD_DTYPE)
+        if len(out):
+            self.lib.pgb_export_records(self.h, _ptr(out))
+        return out
+
+    def import_records(self, records):
+        records = np.ascontiguousarray(records, dtype=RECORD_DTYPE)
+        return int(self.lib.pgb_import_records(self.h, _ptr(records)))
+
     def edges(self):
         n = int(self.lib.pgb_edge_count(self.h))
         out = np.zeros(n, dtype=EDGE_DTYPE)
@@ -206,6 +233,18 @@ def allgather_verdicts(local, counts, group=None, device=None):
     return [arr[r, :int(counts[r])] for r in range(world)]
 
 
+def allreduce_records(records, group=None, device=None):
+    """Merge the ranks' record buffers (each rank fills only the positions it owns): byte-wise SUM all-reduce."""
+    import torch
+    import torch.distributed as dist
+
+    t = torch.from_numpy(records.view(np.uint8).reshape(-1).copy())
+    if device is not None:
+        t = t.to(device, non_blocking=True)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy().view(RECORD_DTYPE)
+
+
 class PoseGraph:
     """Result container: committed edges in commit order (pose_graph.h:62-106)."""
 
@@ -254,9 +293,11 @@ class PoseGraphBuilder:
         self.prefetch_fallback = prefetch_fallback
         self.fallback_wave = fallback_wave
         self.group, self.rank, self.world = group, rank, world_size
-        # overlap the hypothesis-independent fallback (second context, own stream) with the sequential waves;
-        # single-rank only: with several ranks the prefetch is sharded and all-gathered up front instead
-        self.overlap = bool(overlap_fallback and prefetch_fallback and world_size == 1)
+        # overlap the hypothesis-independent fallback (second context, own low-priority stream, driven by a worker
+        # thread) with the sequential waves; with several ranks the worker exchanges each chunk's verdicts over its own
+        # gloo group so that it never shares a communicator with the wave loop
+        self.overlap = bool(overlap_fallback and prefetch_fallback)
+        self.pf_group = None
         self.engine = None
         self.engine_fb = None
         self.timing = {}
@@ -275,6 +316,9 @@ class PoseGraphBuilder:
             if self.engine_fb is None:
                 self.engine_fb = _engine.Engine(device=self.device, min_inliers=self.min_inliers, background=True)
             self.engine_fb.share_pairs(self.engine)
+            if self.world > 1 and self.pf_group is None:
+                import torch.distributed as dist
+                self.pf_group = dist.new_group(backend="gloo")
 
     def engine_stats(self):
         st = self.engine.stats()
@@ -337,13 +381,25 @@ class PoseGraphBuilder:
 
             def prefetch_worker():
                 try:
-                    for s in range(0, Q, self.fallback_wave):
-                        ids = queue[s:s + self.fallback_wave]
+                    chunk = self.fallback_wave * self.world
+                    for s in range(0, Q, chunk):
+                        ids = queue[s:s + chunk]
                         ids = ids[ids != np.uint32(0xFFFFFFFF)]
-                        v = self.engine_fb.run_wave(ids, None, None, flags=WAVE_FALLBACK) if len(ids) else np.zeros(0, dtype=VERDICT_DTYPE)
+                        own = owner_of(ids, self.bounds) if self.world > 1 else np.zeros(len(ids), dtype=np.int64)
+                        mine = ids[own == self.rank] if self.world > 1 else ids
+                        v = (self.engine_fb.run_wave((mine - np.uint32(self.lo)).astype(np.uint32), None, None, flags=WAVE_FALLBACK)
+                             if len(mine) else np.zeros(0, dtype=VERDICT_DTYPE))
+                        v["pair_id"] += np.uint32(self.lo)
+                        if self.world > 1:  # every rank needs every pair's fallback verdict (predictions + commit)
+                            counts = [int(np.count_nonzero(own == r)) for r in range(self.world)]
+                            parts = allgather_verdicts(v, counts, self.pf_group, None)
+                            merged = np.zeros(len(ids), dtype=VERDICT_DTYPE)
+                            for r in range(self.world):
+                                merged[np.nonzero(own == r)[0]] = parts[r]
+                            v = merged
                         with progress:
                             host.set_fallback_verdicts_some(ids, v)
-                            state["done_pos"] = min(Q, s + self.fallback_wave)
+                            state["done_pos"] = min(Q, s + chunk)
                             progress.notify_all()
                 except Exception as exc:  # surface engine failures in the main thread
                     with progress:
@@ -357,6 +413,13 @@ class PoseGraphBuilder:
             self._prefetch(host)
         t_pre = time.perf_counter()
         flags = WAVE_PATH if self.prefetch_fallback else (WAVE_PATH | WAVE_FALLBACK)
+        if self.world > 1:
+            host.set_partition(self.rank, self.world, self.bounds)
+        prof = dict(engine_s=0.0, exchange_s=0.0, host_s=0.0, wait_prefetch_s=0.0, engine_rounds=0, exchanges=0)
+        dev = None
+        if self.world > 1:
+            import torch
+            dev = torch.device("cuda", self.device) if torch.cuda.is_available() else None
         while True:
             with progress:
                 remaining = host.remaining()
@@ -364,35 +427,49 @@ class PoseGraphBuilder:
                     break
                 if worker is not None:
                     need = min(Q, (Q - remaining) + self.wave_size)
+                    t_w = time.perf_counter()
                     while state["done_pos"] < need:
                         progress.wait()
+                    prof["wait_prefetch_s"] += time.perf_counter() - t_w
                     if state["error"] is not None:
                         raise state["error"]
+                t_h = time.perf_counter()
                 items = host.next_wave(self.wave_size)
-            todo = np.nonzero(items["need_gpu"])[0]
-            verdicts = np.zeros(len(todo), dtype=VERDICT_DTYPE)
-            if len(todo):
-                pid = items["pair_id"][todo]
-                own = owner_of(pid, self.bounds)
-                mine = np.nonzero(own == self.rank)[0]
-                local = np.zeros(0, dtype=VERDICT_DTYPE)
-                if len(mine):
-                    sel = todo[mine]
+                status = host.wave_status()
+                prof["host_s"] += time.perf_counter() - t_h
+            # drive the open wave to its fixed point: engine rounds for the positions this rank owns, record exchange
+            # between ranks after every round (multi-rank only)
+            while status != WAVE_DONE:
+                t_a = time.perf_counter()
+                if status == WAVE_NEED_GPU:
+                    sel = np.nonzero(items["need_gpu"])[0]
                     hoff = np.zeros(len(sel) + 1, dtype=np.uint32)
                     hoff[1:] = np.cumsum(items["has_hyp"][sel])
                     hyp = items["hyp"][sel][items["has_hyp"][sel] > 0]
-                    local = self.engine.run_wave((items["pair_id"][sel] - self.lo).astype(np.uint32), hoff, hyp, flags=flags)
-                    local["pair_id"] += np.uint32(self.lo)
-                counts = [int(np.count_nonzero(own == r)) for r in range(self.world)]
-                parts = self._exchange(local, counts)
-                for r in range(self.world):
-                    verdicts[np.nonzero(own == r)[0]] = parts[r]
-            with progress:
-                host.commit_wave(verdicts)  # 0 while the wave still iterates towards its fixed point
+                    verdicts = self.engine.run_wave((items["pair_id"][sel] - self.lo).astype(np.uint32), hoff, hyp, flags=flags)
+                    verdicts["pair_id"] += np.uint32(self.lo)
+                    t_b = time.perf_counter()
+                    prof["engine_s"] += t_b - t_a
+                    prof["engine_rounds"] += 1
+                    with progress:
+                        host.commit_wave(verdicts)
+                    prof["host_s"] += time.perf_counter() - t_b
+                else:  # WAVE_NEED_EXCHANGE
+                    merged = allreduce_records(host.export_records(), self.group, dev)
+                    t_b = time.perf_counter()
+                    prof["exchange_s"] += t_b - t_a
+                    prof["exchanges"] += 1
+                    with progress:
+                        host.import_records(merged)
+                    prof["host_s"] += time.perf_counter() - t_b
+                with progress:
+                    status = host.wave_status()
+                    if status != WAVE_DONE:
+                        items = host.next_wave(self.wave_size)
         if worker is not None:
             worker.join()
         t_end = time.perf_counter()
-        self.timing = dict(register_s=t_reg - t0, prefetch_s=t_pre - t_reg, waves_s=t_end - t_pre, total_s=t_end - t0)
+        self.timing = dict(register_s=t_reg - t0, prefetch_s=t_pre - t_reg, waves_s=t_end - t_pre, total_s=t_end - t0, **prof)
         edges = host.edges()
         self.log = host.log()
         self.counters = host.counters()

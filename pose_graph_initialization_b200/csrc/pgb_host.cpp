@@ -392,6 +392,9 @@ struct Item {
     bool needGpu = false;
     Outcome pred;             // what the overlay currently assumes for this position
     const pgi_verdict *finalV = nullptr, *pathV = nullptr;
+    bool mine = true;         // this rank searches / verifies the position (pair owner); others learn it by exchange
+    bool remoteKnown = false; // a record of the owner has been imported
+    pgi_verdict remoteV;      // the owner's path verdict for the position (remote positions only)
 };
 
 struct HypKey {
@@ -499,6 +502,10 @@ struct pgb_builder {
     std::vector<Item> wave;
     bool waveOpen = false;
     int rounds = 0;
+    int rank = 0, world = 1;
+    std::vector<uint64_t> bounds;  // pair-id ownership: rank r owns [bounds[r], bounds[r+1])
+    int phase = 0;                 // 0 search/resolve, 1 waiting for the record exchange, 2 compare
+    int status = 0;                // PGB_WAVE_* of the open wave
     std::vector<uint32_t> minChangedPos;  // per vertex: smallest wave position whose outcome changed this round
     std::vector<pgi_verdict> fbCache;
     std::vector<uint8_t> fbHave;
@@ -582,7 +589,7 @@ void searchStale(pgb_builder *b, uint32_t limit)
     const double t0 = nowSec();
     std::vector<uint32_t> todo;
     for (uint32_t k = 0; k < b->wave.size() && k < limit; k++)
-        if (!b->wave[k].searched) todo.push_back(k);
+        if (b->wave[k].mine && !b->wave[k].searched) todo.push_back(k);
     if (b->cfg.host_threads <= 1 || todo.size() < 4) {
         for (uint32_t k : todo) searchPosition(b, k, b->scratch[0]);
     } else {
@@ -607,6 +614,7 @@ uint32_t resolveVerdicts(pgb_builder *b)
     uint32_t need = 0;
     for (Item &it : b->wave) {
         it.needGpu = false;
+        if (!it.mine) continue;  // remote positions are resolved by their owner (import)
         it.finalV = it.pathV = nullptr;
         if (it.staticSkip || !it.searched) continue;  // unsearched positions wait for the window to reach them
         if (it.hasHyp) {
@@ -672,27 +680,34 @@ void commitPosition(pgb_builder *b, Item &it)
     if (final->branch == 1) b->ctr.path_accepted++; else b->ctr.fallback_accepted++;
 }
 
-// Iterate the open wave towards its fixed point.  Returns the number of positions committed (0 while the wave
-// still waits for engine verdicts).
+// Iterate the open wave towards its fixed point.  Returns the number of positions committed (0 while the wave still
+// waits for engine verdicts or for the record exchange between ranks); b->status says what it waits for.
 uint32_t advanceWave(pgb_builder *b)
 {
     const uint32_t n = (uint32_t)b->wave.size();
     for (;;) {
-        uint32_t firstStale = n;
-        for (uint32_t k = 0; k < n; k++)
-            if (!b->wave[k].searched) { firstStale = k; break; }
-        // optional re-search window behind the first stale position (0 = unlimited: measured best on cfg2, the
-        // re-search cascade is intrinsic rather than wasted look-ahead)
-        const uint32_t window = b->cfg.reserved > 0 ? (uint32_t)b->cfg.reserved : n;
-        const uint32_t limit = firstStale + window < n ? firstStale + window : n;
-        searchStale(b, limit);
-        if (resolveVerdicts(b) > 0) return 0;  // engine round trip needed; the wave stays open
-        // actual outcomes vs. the predictions the overlay was built from
+        if (b->phase == 0) {
+            uint32_t firstStale = n;
+            for (uint32_t k = 0; k < n; k++)
+                if (b->wave[k].mine && !b->wave[k].searched) { firstStale = k; break; }
+            // optional re-search window behind the first stale position (0 = unlimited: measured best on cfg2, the
+            // re-search cascade is intrinsic rather than wasted look-ahead)
+            const uint32_t window = b->cfg.reserved > 0 ? (uint32_t)b->cfg.reserved : n;
+            const uint32_t limit = firstStale + window < n ? firstStale + window : n;
+            searchStale(b, limit);
+            if (resolveVerdicts(b) > 0) { b->status = PGB_WAVE_NEED_GPU; return 0; }  // engine round trip; wave stays open
+            if (b->world > 1) { b->phase = 1; b->status = PGB_WAVE_NEED_EXCHANGE; return 0; }
+            b->phase = 2;
+        }
+        if (b->phase == 1) { b->status = PGB_WAVE_NEED_EXCHANGE; return 0; }  // waiting for pgb_import_records
+        // ---- phase 2: actual outcomes vs. the predictions the overlay was built from (identical on every rank) ----
         std::fill(b->minChangedPos.begin(), b->minChangedPos.end(), UINT32_MAX);
         uint32_t firstChanged = UINT32_MAX;
+        bool allKnown = true;
         for (uint32_t k = 0; k < n; k++) {
             Item &it = b->wave[k];
-            if (it.staticSkip || !it.searched) continue;
+            if (it.staticSkip) continue;
+            if (it.mine ? !it.searched : !it.remoteKnown) { allKnown = false; continue; }
             const Outcome act = outcomeOf(it.finalV);
             if (!act.sameEdge(it.pred)) {
                 it.pred = act;
@@ -701,17 +716,16 @@ uint32_t advanceWave(pgb_builder *b)
                 b->minChangedPos[it.dst] = std::min(b->minChangedPos[it.dst], k);
             }
         }
+        b->phase = 0;
         if (firstChanged == UINT32_MAX) {
-            bool allSearched = true;
-            for (uint32_t k = limit; k < n && allSearched; k++) allSearched = b->wave[k].searched;
-            if (allSearched) break;  // fixed point: every search saw exactly the sequential graph
+            if (allKnown) break;  // fixed point: every search saw exactly the sequential graph
             ++b->rounds;
-            continue;                // nothing changed inside the window: move it forward
+            continue;             // nothing changed among the known positions: keep searching
         }
         ++b->rounds;
         for (uint32_t m = firstChanged + 1; m < n; m++) {
             Item &it = b->wave[m];
-            if (!it.searched) continue;
+            if (!it.mine || !it.searched) continue;
             for (uint32_t v : it.expanded)
                 if (b->minChangedPos[v] < m) { it.searched = false; break; }
         }
@@ -721,6 +735,7 @@ uint32_t advanceWave(pgb_builder *b)
     for (Item &it : b->wave) commitPosition(b, it);
     b->wave.clear();
     b->waveOpen = false;
+    b->status = PGB_WAVE_DONE;
     b->overlay.clear();
     b->ctr.sec_commit += nowSec() - t0;
     return n;
@@ -848,6 +863,13 @@ uint32_t pgb_next_wave(pgb_builder *b, uint32_t max_items, pgb_item *items)
         } else
             break;
         it.searched = false;
+        it.remoteKnown = false;
+        it.mine = true;
+        if (b->world > 1 && !it.staticSkip) {
+            int owner = 0;
+            while (owner + 1 < b->world && it.pairId >= b->bounds[owner + 1]) ++owner;
+            it.mine = owner == b->rank;
+        }
         // prediction: the pair's hypothesis-independent fallback verdict, if already known
         const bool fbKnown = !it.staticSkip && b->fbHave[it.pairId];
         it.pred = fbKnown ? outcomeOf(&b->fbCache[it.pairId]) : Outcome();
@@ -857,11 +879,11 @@ uint32_t pgb_next_wave(pgb_builder *b, uint32_t max_items, pgb_item *items)
     if (b->wave.empty()) return 0;
     b->waveOpen = true;
     b->rounds = 0;
+    b->phase = 0;
     b->ctr.waves++;
     b->ctr.items_speculated += b->wave.size();
     rebuildOverlay(b);
-    searchStale(b, (uint32_t)b->wave.size());
-    resolveVerdicts(b);
+    advanceWave(b);  // searches, resolves from the caches and stops at the first engine round trip / exchange / commit
     return emitItems(b, items);
 }
 
@@ -885,6 +907,61 @@ uint32_t pgb_commit_wave(pgb_builder *b, const pgi_verdict *verdicts, uint32_t n
             b->fbHave[it.pairId] = 1;
         }
     }
+    return advanceWave(b);
+}
+
+int32_t pgb_set_partition(pgb_builder *b, int32_t rank, int32_t world, const uint64_t *bounds)
+{
+    if (!b || world < 1 || rank < 0 || rank >= world || !bounds || b->waveOpen) return -1;
+    b->rank = rank;
+    b->world = world;
+    b->bounds.assign(bounds, bounds + world + 1);
+    return 0;
+}
+
+int32_t pgb_wave_status(pgb_builder *b) { return (b && b->waveOpen) ? b->status : PGB_WAVE_DONE; }
+uint32_t pgb_wave_size(pgb_builder *b) { return b ? (uint32_t)b->wave.size() : 0; }
+
+// One record per wave position; a rank fills the positions it owns and leaves the others zero, so a byte-wise SUM
+// all-reduce merges the ranks' buffers.
+void pgb_export_records(pgb_builder *b, pgb_record *out)
+{
+    const uint32_t n = (uint32_t)b->wave.size();
+    memset(out, 0, (size_t)n * sizeof(pgb_record));
+    for (uint32_t k = 0; k < n; k++) {
+        const Item &it = b->wave[k];
+        if (!it.mine || it.staticSkip) continue;
+        pgb_record &r = out[k];
+        r.valid = (it.searched && it.finalV) ? 1 : 0;
+        r.has_hyp = it.hasHyp;
+        r.has_path_verdict = it.pathV ? 1 : 0;
+        r.final_is_path = (it.pathV && it.finalV == it.pathV) ? 1 : 0;
+        r.touched = it.touched;
+        if (it.pathV) r.v = *it.pathV;
+    }
+}
+
+uint32_t pgb_import_records(pgb_builder *b, const pgb_record *in)
+{
+    if (!b || !b->waveOpen || b->phase != 1) return 0;
+    const uint32_t n = (uint32_t)b->wave.size();
+    for (uint32_t k = 0; k < n; k++) {
+        Item &it = b->wave[k];
+        if (it.mine || it.staticSkip) continue;
+        const pgb_record &r = in[k];
+        it.remoteKnown = r.valid != 0;
+        it.hasHyp = r.has_hyp != 0;
+        it.touched = r.touched;
+        it.pathV = it.finalV = nullptr;
+        if (r.has_path_verdict) { it.remoteV = r.v; it.pathV = &it.remoteV; }
+        if (r.final_is_path)
+            it.finalV = &it.remoteV;
+        else if (b->fbHave[it.pairId])
+            it.finalV = &b->fbCache[it.pairId];
+        else
+            it.remoteKnown = false;  // (cannot happen: with several ranks the fallback verdicts are prefetched)
+    }
+    b->phase = 2;
     return advanceWave(b);
 }
 

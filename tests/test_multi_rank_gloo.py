@@ -1,6 +1,7 @@
-"""N > 1 host path on CPU: two ranks (gloo) shard the pairs by owner, each produces verdicts for the wave items it owns
-(oracle stand-in for the engine — tests only), the 160-byte records are all-gathered, and BOTH ranks must commit the
-pose graph the single-process sequential oracle commits (SPMD host)."""
+"""N > 1 host path on CPU: two ranks (gloo) shard the pairs by owner; each rank runs the A* searches and produces the
+verdicts (oracle stand-in for the engine — tests only) for the wave positions it owns, the per-position records are
+merged with one all-reduce per round, and BOTH ranks must commit the pose graph the single-process sequential oracle
+commits (SPMD host)."""
 import os
 import sys
 
@@ -36,16 +37,23 @@ def _worker(rank, world, port, ret):
         mine[k] = eng.verdict(p, None, path=False, fallback=True)
     parts = B.allgather_verdicts(mine, [int(bounds[r + 1] - bounds[r]) for r in range(world)])
     host.set_fallback_verdicts(np.concatenate(parts))
+    host.set_partition(rank, world, bounds)  # each rank searches and verifies only the positions it owns
+    exchanges = 0
     while host.remaining() > 0:
         items = host.next_wave(64)
-        todo = np.nonzero(items["need_gpu"])[0]
-        own = B.owner_of(items["pair_id"][todo], bounds)
-        local = eng.run_items(items[todo[own == rank]], path=True, fallback=False)
-        parts = B.allgather_verdicts(local, [int(np.count_nonzero(own == r)) for r in range(world)])
-        verdicts = np.zeros(len(todo), dtype=B.VERDICT_DTYPE)
-        for r in range(world):
-            verdicts[np.nonzero(own == r)[0]] = parts[r]
-        host.commit_wave(verdicts)
+        status = host.wave_status()
+        while status != B.WAVE_DONE:
+            if status == B.WAVE_NEED_GPU:
+                todo = items[items["need_gpu"] > 0]
+                assert np.all(B.owner_of(todo["pair_id"], bounds) == rank)  # only own positions are ever requested
+                host.commit_wave(eng.run_items(todo, path=True, fallback=False))
+            else:
+                host.import_records(B.allreduce_records(host.export_records()))
+                exchanges += 1
+            status = host.wave_status()
+            if status != B.WAVE_DONE:
+                items = host.next_wave(64)
+    assert exchanges > 0
     edges = host.edges()
     olog, ostats = O.run_scene(sc, sim_threshold=0.0)
     committed = olog[olog["committed"] > 0]
