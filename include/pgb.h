@@ -114,11 +114,11 @@ uint32_t pgb_next_wave(pgb_builder *b, uint32_t max_items, pgb_item *items);
  * (accepted, rejected or skipped); the rest were re-queued. */
 uint32_t pgb_commit_wave(pgb_builder *b, const pgi_verdict *verdicts, uint32_t n_verdicts);
 
-/* Multi-rank (SPMD, one process per GPU): rank r searches and verifies only the positions whose pair id lies in
- * [bounds[r], bounds[r+1]); after each round the ranks exchange pgb_record arrays (pgb_export_records -> byte-wise
+/* Multi-rank (SPMD, one process per GPU): rank r searches and verifies only the positions whose pair id is
+ * congruent to r modulo world (interleaved ownership keeps every wave balanced); after each round the ranks exchange pgb_record arrays (pgb_export_records -> byte-wise
  * SUM all-reduce -> pgb_import_records) so that every rank applies the same outcomes and commits the same graph.
  * pgb_wave_status tells the driver what the open wave waits for. */
-int32_t pgb_set_partition(pgb_builder *b, int32_t rank, int32_t world, const uint64_t *bounds);
+int32_t pgb_set_partition(pgb_builder *b, int32_t rank, int32_t world);
 int32_t pgb_wave_status(pgb_builder *b);
 uint32_t pgb_wave_size(pgb_builder *b);
 void pgb_export_records(pgb_builder *b, pgb_record *out);

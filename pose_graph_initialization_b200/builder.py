@@ -148,9 +148,8 @@ class HostBuilder:
         verdicts = np.ascontiguousarray(verdicts, dtype=VERDICT_DTYPE)
         return int(self.lib.pgb_commit_wave(self.h, _ptr(verdicts), C.c_uint32(len(verdicts))))
 
-    def set_partition(self, rank, world, bounds):
-        bounds = np.ascontiguousarray(bounds, dtype=np.uint64)
-        if self.lib.pgb_set_partition(self.h, C.c_int32(rank), C.c_int32(world), _ptr(bounds)) != 0:
+    def set_partition(self, rank, world):
+        if self.lib.pgb_set_partition(self.h, C.c_int32(rank), C.c_int32(world)) != 0:
             raise RuntimeError("pgb_set_partition failed")
 
     def wave_status(self):
@@ -193,22 +192,30 @@ class HostBuilder:
 
 
 # ---- pair ownership / verdict exchange ------------------------------------------------------
-def owner_ranges(n_pairs, world_size):
-    """Contiguous, balanced pair-id ranges: rank r owns [bounds[r], bounds[r+1])."""
-    return np.array([(n_pairs * r) // world_size for r in range(world_size + 1)], dtype=np.int64)
+def owner_of(pair_ids, world_size):
+    """Interleaved ownership: pair p belongs to rank p % world (consecutive queue positions share views, so
+    contiguous ranges would leave most ranks idle within a wave)."""
+    return np.asarray(pair_ids, dtype=np.int64) % world_size
 
 
-def owner_of(pair_ids, bounds):
-    return np.searchsorted(bounds, np.asarray(pair_ids, dtype=np.int64), side="right") - 1
+def local_id(pair_ids, world_size):
+    return (np.asarray(pair_ids, dtype=np.int64) // world_size).astype(np.uint32)
 
 
-def shard_scene(scene, lo, hi):
-    """The sub-scene whose pair list is scene pairs [lo, hi) (keypoints of all views are kept)."""
+def shard_scene(scene, rank, world_size):
+    """The sub-scene holding the pairs rank `rank` owns (pairs rank, rank + world, ...; keypoints of all views kept).
+    Local pair id = global id // world."""
     sub = dict(scene)
-    mo = np.asarray(scene["m_offset"], dtype=np.uint64)
-    sub["pair_views"] = scene["pair_views"][lo:hi]
-    sub["m_offset"] = mo[lo:hi + 1] - mo[lo]
-    sub["matches"] = scene["matches"][int(mo[lo]):int(mo[hi])]
+    mo = np.asarray(scene["m_offset"], dtype=np.int64)
+    ids = np.arange(rank, len(scene["pair_views"]), world_size)
+    sub["pair_views"] = np.ascontiguousarray(scene["pair_views"][ids])
+    n = mo[ids + 1] - mo[ids]
+    sub["m_offset"] = np.concatenate([[0], np.cumsum(n)]).astype(np.uint64)
+    if len(ids) and np.all(n == n[0]) and np.all(np.diff(mo) == n[0]):  # equal-sized pairs: strided view, one copy
+        sub["matches"] = np.ascontiguousarray(np.asarray(scene["matches"]).reshape(len(mo) - 1, int(n[0]), 2)[rank::world_size]).reshape(-1, 2)
+    else:
+        rows = np.concatenate([np.arange(mo[i], mo[i + 1]) for i in ids]) if len(ids) else np.zeros(0, dtype=np.int64)
+        sub["matches"] = np.ascontiguousarray(np.asarray(scene["matches"])[rows])
     return sub
 
 
@@ -304,14 +311,11 @@ class PoseGraphBuilder:
 
     # -- engine + registration (H2D inside, counted by the engine's stats) -----------------------------------
     def prepare(self):
-        P = len(self.scene["pair_views"])
-        self.bounds = owner_ranges(P, self.world)
-        lo, hi = int(self.bounds[self.rank]), int(self.bounds[self.rank + 1])
-        self.lo, self.hi = lo, hi
         if self.engine is None:
             self.engine = _engine.Engine(device=self.device, min_inliers=self.min_inliers)
-        sub = self.scene if self.world == 1 else shard_scene(self.scene, lo, hi)
+        sub = self.scene if self.world == 1 else shard_scene(self.scene, self.rank, self.world)
         self.engine.register_scene(sub, self.thr_px)
+        self.prepared = True
         if self.overlap:
             if self.engine_fb is None:
                 self.engine_fb = _engine.Engine(device=self.device, min_inliers=self.min_inliers, background=True)
@@ -349,23 +353,24 @@ class PoseGraphBuilder:
         """Fallback verdicts are a pure function of the pair: compute them for every owned pair in big waves,
         all-gather once, hand them to the host."""
         P = len(self.scene["pair_views"])
-        mine = np.arange(self.lo, self.hi, dtype=np.uint32)
+        mine = np.arange(self.rank, P, self.world, dtype=np.int64)
         out = np.zeros(len(mine), dtype=VERDICT_DTYPE)
         for s in range(0, len(mine), self.fallback_wave):
-            ids = mine[s:s + self.fallback_wave] - self.lo
-            out[s:s + len(ids)] = self.engine.run_wave(ids.astype(np.uint32), None, None, flags=WAVE_FALLBACK)
-        out["pair_id"] += np.uint32(self.lo)
-        counts = [int(self.bounds[r + 1] - self.bounds[r]) for r in range(self.world)]
+            ids = local_id(mine[s:s + self.fallback_wave], self.world)
+            out[s:s + len(ids)] = self.engine.run_wave(ids, None, None, flags=WAVE_FALLBACK)
+        out["pair_id"] = mine.astype(np.uint32)
+        counts = [len(range(r, P, self.world)) for r in range(self.world)]
         parts = self._exchange(out, counts)
-        allv = np.concatenate(parts) if self.world > 1 else out
-        assert len(allv) == P
+        allv = np.zeros(P, dtype=VERDICT_DTYPE)
+        for r in range(self.world):
+            allv[r::self.world] = parts[r]
         host.set_fallback_verdicts(allv)
         return allv
 
     def run(self, reconstruction_=None, poseGraph_=None):
         """PoseGraphBuilder::run (pose_graph_builder.h:173-239) -> PoseGraph."""
         t0 = time.perf_counter()
-        if self.engine is None or getattr(self, "bounds", None) is None:
+        if self.engine is None or not getattr(self, "prepared", False):
             self.prepare()
         t_reg = time.perf_counter()
         host = HostBuilder(self.scene, lazy_fallback=not self.prefetch_fallback, **self.cfg)
@@ -385,11 +390,11 @@ class PoseGraphBuilder:
                     for s in range(0, Q, chunk):
                         ids = queue[s:s + chunk]
                         ids = ids[ids != np.uint32(0xFFFFFFFF)]
-                        own = owner_of(ids, self.bounds) if self.world > 1 else np.zeros(len(ids), dtype=np.int64)
-                        mine = ids[own == self.rank] if self.world > 1 else ids
-                        v = (self.engine_fb.run_wave((mine - np.uint32(self.lo)).astype(np.uint32), None, None, flags=WAVE_FALLBACK)
+                        own = owner_of(ids, self.world)
+                        mine = ids[own == self.rank]
+                        v = (self.engine_fb.run_wave(local_id(mine, self.world), None, None, flags=WAVE_FALLBACK)
                              if len(mine) else np.zeros(0, dtype=VERDICT_DTYPE))
-                        v["pair_id"] += np.uint32(self.lo)
+                        v["pair_id"] = mine.astype(np.uint32)
                         if self.world > 1:  # every rank needs every pair's fallback verdict (predictions + commit)
                             counts = [int(np.count_nonzero(own == r)) for r in range(self.world)]
                             parts = allgather_verdicts(v, counts, self.pf_group, None)
@@ -414,7 +419,7 @@ class PoseGraphBuilder:
         t_pre = time.perf_counter()
         flags = WAVE_PATH if self.prefetch_fallback else (WAVE_PATH | WAVE_FALLBACK)
         if self.world > 1:
-            host.set_partition(self.rank, self.world, self.bounds)
+            host.set_partition(self.rank, self.world)
         prof = dict(engine_s=0.0, exchange_s=0.0, host_s=0.0, wait_prefetch_s=0.0, engine_rounds=0, exchanges=0)
         dev = None
         if self.world > 1:
@@ -446,8 +451,8 @@ class PoseGraphBuilder:
                     hoff = np.zeros(len(sel) + 1, dtype=np.uint32)
                     hoff[1:] = np.cumsum(items["has_hyp"][sel])
                     hyp = items["hyp"][sel][items["has_hyp"][sel] > 0]
-                    verdicts = self.engine.run_wave((items["pair_id"][sel] - self.lo).astype(np.uint32), hoff, hyp, flags=flags)
-                    verdicts["pair_id"] += np.uint32(self.lo)
+                    verdicts = self.engine.run_wave(local_id(items["pair_id"][sel], self.world), hoff, hyp, flags=flags)
+                    verdicts["pair_id"] = items["pair_id"][sel]
                     t_b = time.perf_counter()
                     prof["engine_s"] += t_b - t_a
                     prof["engine_rounds"] += 1

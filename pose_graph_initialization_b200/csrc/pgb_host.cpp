@@ -503,7 +503,6 @@ struct pgb_builder {
     bool waveOpen = false;
     int rounds = 0;
     int rank = 0, world = 1;
-    std::vector<uint64_t> bounds;  // pair-id ownership: rank r owns [bounds[r], bounds[r+1])
     int phase = 0;                 // 0 search/resolve, 1 waiting for the record exchange, 2 compare
     int status = 0;                // PGB_WAVE_* of the open wave
     std::vector<uint32_t> minChangedPos;  // per vertex: smallest wave position whose outcome changed this round
@@ -866,9 +865,7 @@ uint32_t pgb_next_wave(pgb_builder *b, uint32_t max_items, pgb_item *items)
         it.remoteKnown = false;
         it.mine = true;
         if (b->world > 1 && !it.staticSkip) {
-            int owner = 0;
-            while (owner + 1 < b->world && it.pairId >= b->bounds[owner + 1]) ++owner;
-            it.mine = owner == b->rank;
+            it.mine = (int)(it.pairId % (uint32_t)b->world) == b->rank;  // interleaved ownership balances every wave
         }
         // prediction: the pair's hypothesis-independent fallback verdict, if already known
         const bool fbKnown = !it.staticSkip && b->fbHave[it.pairId];
@@ -910,12 +907,11 @@ uint32_t pgb_commit_wave(pgb_builder *b, const pgi_verdict *verdicts, uint32_t n
     return advanceWave(b);
 }
 
-int32_t pgb_set_partition(pgb_builder *b, int32_t rank, int32_t world, const uint64_t *bounds)
+int32_t pgb_set_partition(pgb_builder *b, int32_t rank, int32_t world)
 {
-    if (!b || world < 1 || rank < 0 || rank >= world || !bounds || b->waveOpen) return -1;
+    if (!b || world < 1 || rank < 0 || rank >= world || b->waveOpen) return -1;
     b->rank = rank;
     b->world = world;
-    b->bounds.assign(bounds, bounds + world + 1);
     return 0;
 }
 

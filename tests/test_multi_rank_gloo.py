@@ -25,19 +25,23 @@ def _worker(rank, world, port, ret):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     sc = S.make_scene(n_views=9, n_corr=150, outlier_ratio=0.3, seed=11, n_points=500)
     P = len(sc["pair_views"])
-    bounds = B.owner_ranges(P, world)
-    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
-    sub = B.shard_scene(sc, lo, hi)
-    assert len(sub["pair_views"]) == hi - lo and int(sub["m_offset"][-1]) == len(sub["matches"])
+    sub = B.shard_scene(sc, rank, world)  # pairs rank, rank + world, ... (interleaved ownership)
+    mine_ids = np.arange(rank, P, world)
+    assert len(sub["pair_views"]) == len(mine_ids) and int(sub["m_offset"][-1]) == len(sub["matches"])
+    assert np.array_equal(sub["pair_views"], sc["pair_views"][mine_ids])
+    assert np.array_equal(sub["matches"][:150], sc["matches"][int(sc["m_offset"][rank]):int(sc["m_offset"][rank]) + 150])
     eng = OracleEngine(O, sc)  # verdicts only for owned pairs
     host = B.HostBuilder(sc, similarity_threshold=0.0, host_threads=2, lazy_fallback=False)
     # sharded prefetch + one all-gather
-    mine = np.zeros(hi - lo, dtype=B.VERDICT_DTYPE)
-    for k, p in enumerate(range(lo, hi)):
-        mine[k] = eng.verdict(p, None, path=False, fallback=True)
-    parts = B.allgather_verdicts(mine, [int(bounds[r + 1] - bounds[r]) for r in range(world)])
-    host.set_fallback_verdicts(np.concatenate(parts))
-    host.set_partition(rank, world, bounds)  # each rank searches and verifies only the positions it owns
+    mine = np.zeros(len(mine_ids), dtype=B.VERDICT_DTYPE)
+    for k, p in enumerate(mine_ids):
+        mine[k] = eng.verdict(int(p), None, path=False, fallback=True)
+    parts = B.allgather_verdicts(mine, [len(range(r, P, world)) for r in range(world)])
+    allv = np.zeros(P, dtype=B.VERDICT_DTYPE)
+    for r in range(world):
+        allv[r::world] = parts[r]
+    host.set_fallback_verdicts(allv)
+    host.set_partition(rank, world)  # each rank searches and verifies only the positions it owns
     exchanges = 0
     while host.remaining() > 0:
         items = host.next_wave(64)
@@ -45,7 +49,7 @@ def _worker(rank, world, port, ret):
         while status != B.WAVE_DONE:
             if status == B.WAVE_NEED_GPU:
                 todo = items[items["need_gpu"] > 0]
-                assert np.all(B.owner_of(todo["pair_id"], bounds) == rank)  # only own positions are ever requested
+                assert np.all(B.owner_of(todo["pair_id"], world) == rank)  # only own positions are ever requested
                 host.commit_wave(eng.run_items(todo, path=True, fallback=False))
             else:
                 host.import_records(B.allreduce_records(host.export_records()))
@@ -81,9 +85,8 @@ def test_two_ranks_commit_the_sequential_graph():
     assert ret[0][1] > 0 and ret[1][1] > 0
 
 
-def test_owner_ranges_and_shards():
+def test_interleaved_ownership():
     from pose_graph_initialization_b200 import builder as B
 
-    b = B.owner_ranges(10, 4)
-    assert list(b) == [0, 2, 5, 7, 10]
-    assert list(B.owner_of([0, 1, 2, 4, 5, 9], b)) == [0, 0, 1, 1, 2, 3]
+    assert list(B.owner_of([0, 1, 2, 4, 5, 9], 4)) == [0, 1, 2, 0, 1, 1]
+    assert list(B.local_id([0, 1, 2, 4, 5, 9], 4)) == [0, 0, 0, 1, 1, 2]
