@@ -573,11 +573,43 @@ __device__ inline void smallestEigvec9Warp(double *A /*81 shared*/, double *V /*
 
 // Least-squares refit on the inliers of Ecur (8-point normal equations in 2^-40 fixed point, essential projection).
 // Whole CTA cooperates; result in shared sEls / *sOk (valid after the trailing __syncthreads).
-__device__ inline void lsRefitBlock(const double4 *rows, uint32_t N, const double Ecur[9], double thrSq, long long *sAcc /*45*/,
-                                    double *sM /*81*/, double *sV /*81*/, uint32_t *sWarpU, double *sEls /*9*/, int *sOk)
+// Pass A marks the inliers once (FP32 certificate first: a point certified outside the truncation band is outside the
+// tighter inlier band too; exact FP64 residual otherwise) into a shared bit mask; the accumulation passes only visit
+// marked points.
+template <bool USE_F32>
+__device__ inline void lsRefitBlock(const double4 *rows, const float4 *pts, uint32_t N, const double Ecur[9], double thrSq,
+                                    float rOut, uint32_t *sInlBits /*ceil(N/32)*/, long long *sAcc /*45*/, double *sM /*81*/,
+                                    double *sV /*81*/, uint32_t *sWarpU, double *sEls /*9*/, int *sOk)
 {
     if (threadIdx.x < 45) sAcc[threadIdx.x] = 0;
     uint32_t cntLocal = 0;
+    {
+        float Ef[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) Ef[k] = (float)Ecur[k];
+        const uint32_t nRound = (N + 31u) & ~31u;
+        for (uint32_t i = threadIdx.x; i < nRound; i += kCtaThreads) {
+            bool in = false;
+            if (i < N) {
+                bool maybe = true;
+                if (USE_F32) {
+                    const float4 p = pts[i];
+                    const float rxc = fmaf(Ef[0], p.z, fmaf(Ef[3], p.w, Ef[6]));
+                    const float ryc = fmaf(Ef[1], p.z, fmaf(Ef[4], p.w, Ef[7]));
+                    const float rwc = fmaf(Ef[2], p.z, fmaf(Ef[5], p.w, Ef[8]));
+                    const float r = fmaf(p.x, rxc, fmaf(p.y, ryc, rwc));
+                    maybe = !(fabsf(r) > rOut);
+                }
+                if (maybe) {
+                    const double4 c = rows[i];
+                    in = sampsonSq(c.x, c.y, c.z, c.w, Ecur) < thrSq;
+                }
+            }
+            const uint32_t word = __ballot_sync(0xffffffffu, in);
+            if ((threadIdx.x & 31) == 0) sInlBits[i >> 5] = word;
+            cntLocal += in ? 1u : 0u;
+        }
+    }
     __syncthreads();
     // 3 sub-passes x 15 upper-triangular entries keep the accumulators in registers
 #pragma unroll 1
@@ -586,9 +618,8 @@ __device__ inline void lsRefitBlock(const double4 *rows, uint32_t N, const doubl
 #pragma unroll
         for (int e = 0; e < 15; e++) acc[e] = 0;
         for (uint32_t i = threadIdx.x; i < N; i += kCtaThreads) {
+            if (!((sInlBits[i >> 5] >> (i & 31)) & 1u)) continue;
             const double4 c = rows[i];
-            if (!(sampsonSq(c.x, c.y, c.z, c.w, Ecur) < thrSq)) continue;
-            if (sp == 0) cntLocal++;
             const double av[9] = {c.z * c.x, c.z * c.y, c.z, c.w * c.x, c.w * c.y, c.w, c.x, c.y, 1.0};
             // entries e = 15 sp .. 15 sp + 14 of the row-major upper triangle (r <= q)
             int e = 0;
@@ -654,7 +685,7 @@ __device__ inline void lsRefitBlock(const double4 *rows, uint32_t N, const doubl
 // ---------------------------------------------------------------------------------------------
 template <bool USE_F32>
 __device__ __forceinline__ void k5Body(const WaveArgs &a, int chunk, int lastChunk, uint32_t w, float4 *sPts, uint16_t *sQueueAll,
-                                       uint32_t queueStride)
+                                       uint32_t queueStride, uint32_t *sInlBits)
 {
     SlotState &st = a.state[w];
     const uint32_t flags0 = st.flags;
@@ -672,7 +703,7 @@ __device__ __forceinline__ void k5Body(const WaveArgs &a, int chunk, int lastChu
     __shared__ float4 sElsF[3];
     __shared__ unsigned long long sCost[kBatch][10], sLoCost;
     __shared__ uint32_t sInl[kBatch][10], sLoInl, sModels;
-    __shared__ int sNextB;
+    __shared__ int sNextB, sNextPass, sPassStart[kBatch + 1];
     __shared__ float sMaxB[8], sMaxD[8];
     __shared__ long long sAcc[45];
     __shared__ double sM[81], sV[81], sEls[9], sBestE[9];
@@ -728,26 +759,41 @@ __device__ __forceinline__ void k5Body(const WaveArgs &a, int chunk, int lastChu
             // ---- phase 1: score every model of the next kBatch iterations (pure functions of the models) ----------
             int nb = itEnd - it < kBatch ? itEnd - it : kBatch;
             nb = sMaxIters - it < nb ? sMaxIters - it : nb;
-            int pass = 0;  // running index of (iteration, model pair) passes of this batch; warp = pass mod 8
-            for (int bI = 0; bI < nb; bI++) {
+            // (iteration, model pair) passes of the batch are handed to the warps dynamically (shared counter): models
+            // with many near-inliers take longer in the exact path, a static split left warps idle at the barrier
+            if (threadIdx.x == 0) {
+                int acc = 0;
+                for (int bI = 0; bI < nb; bI++) {
+                    sPassStart[bI] = acc;
+                    acc += (a.fbCounts[(size_t)w * kFbChunk + (it + bI - chunk * kFbChunk)] + 1) / 2;
+                }
+                sPassStart[nb] = acc;
+                sNextPass = 0;
+            }
+            __syncthreads();
+            for (;;) {
+                int pass = 0;
+                if (lane == 0) pass = atomicAdd(&sNextPass, 1);
+                pass = __shfl_sync(0xffffffffu, pass, 0);
+                if (pass >= sPassStart[nb]) break;
+                int bI = 0;
+                while (pass >= sPassStart[bI + 1]) ++bI;
+                const int q = 2 * (pass - sPassStart[bI]);
                 const int j = it + bI - chunk * kFbChunk;
                 const int ns = a.fbCounts[(size_t)w * kFbChunk + j];
                 const double *sols = a.fbSols + ((size_t)w * kFbChunk + j) * 90;
                 const float4 *solsF = a.fbSolsF + ((size_t)w * kFbChunk + j) * 30;
-                for (int q = 0; q < ns; q += 2, ++pass) {
-                    if ((pass & 7) != warp) continue;
-                    unsigned long long c[2];
-                    uint32_t n[2];
-                    const bool two = q + 1 < ns;
-                    scoreModelsWarp<USE_F32>(rows, sPts, N, sols + q * 9, two ? sols + (q + 1) * 9 : nullptr, solsF + q * 3, thrSq,
-                                             truncSq, invT, fc.rOut, sQueue, c, n);
-                    if (lane == 0) {
-                        sCost[bI][q] = c[0];
-                        sInl[bI][q] = n[0];
-                        if (two) {
-                            sCost[bI][q + 1] = c[1];
-                            sInl[bI][q + 1] = n[1];
-                        }
+                unsigned long long c[2];
+                uint32_t n[2];
+                const bool two = q + 1 < ns;
+                scoreModelsWarp<USE_F32>(rows, sPts, N, sols + q * 9, two ? sols + (q + 1) * 9 : nullptr, solsF + q * 3, thrSq, truncSq,
+                                         invT, fc.rOut, sQueue, c, n);
+                if (lane == 0) {
+                    sCost[bI][q] = c[0];
+                    sInl[bI][q] = n[0];
+                    if (two) {
+                        sCost[bI][q + 1] = c[1];
+                        sInl[bI][q + 1] = n[1];
                     }
                 }
             }
@@ -781,7 +827,7 @@ __device__ __forceinline__ void k5Body(const WaveArgs &a, int chunk, int lastChu
                     double Eb[9];
 #pragma unroll
                     for (int k = 0; k < 9; k++) Eb[k] = sBestE[k];
-                    lsRefitBlock(rows, N, Eb, thrSq, sAcc, sM, sV, sWarpU, sEls, &sOk);
+                    lsRefitBlock<USE_F32>(rows, sPts, N, Eb, thrSq, fc.rOut, sInlBits, sAcc, sM, sV, sWarpU, sEls, &sOk);
                     if (!sOk) break;
                     if (threadIdx.x == 0) {
                         sElsF[0] = make_float4((float)sEls[0], (float)sEls[1], (float)sEls[2], (float)sEls[3]);
@@ -888,10 +934,12 @@ __global__ void __launch_bounds__(kCtaThreads, 3) k5_fallback_score(WaveArgs a, 
     // dynamic shared memory: smemPts float4 points, then 8 per-warp queues of min(smemPts, 2048) uint16 indices
     const uint32_t queueStride = smemPts < 2048u ? ((smemPts + 31u) & ~31u) : 2048u;
     uint16_t *sQueueAll = reinterpret_cast<uint16_t *>(sPts + smemPts);
+    // inlier bit mask of the LO refit: after the queues (staged pairs) or in global scratch-free form for huge pairs
+    uint32_t *sInlBits = reinterpret_cast<uint32_t *>(sQueueAll + 8 * (size_t)queueStride);
     if (N <= smemPts)
-        k5Body<true>(a, chunk, lastChunk, w, sPts, sQueueAll, queueStride);
+        k5Body<true>(a, chunk, lastChunk, w, sPts, sQueueAll, queueStride, sInlBits);
     else
-        k5Body<false>(a, chunk, lastChunk, w, sPts, sQueueAll, queueStride);  // pair too large to stage: exact FP64 for every point
+        k5Body<false>(a, chunk, lastChunk, w, sPts, sQueueAll, queueStride, a.bits + (size_t)w * 2 * a.bitsStride);  // pair too large to stage: exact FP64 for every point; the (unused) path bit buffers hold the mask
 }
 
 // Whole-CTA E -> candidates -> triangulation vote (pose_utils.h:172-240).  Results in shared memory.
