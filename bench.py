@@ -225,8 +225,11 @@ def main():
     ev0.record()
     t0 = time.perf_counter()
     counters = None
+    step_wall = {"resident": [], "e2e": []}
     for _ in range(args.steps):
+        ts = time.perf_counter()
         graph = pgb.run()
+        step_wall["resident"].append(round((time.perf_counter() - ts) * 1e3, 1))
         counters = pgb.counters
     barrier()
     ev1.record()
@@ -243,9 +246,11 @@ def main():
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev2.record()
     for _ in range(args.steps):
+        ts = time.perf_counter()
         pgb.prepare()
         graph = pgb.run()
         n_edges = graph.numEdges()
+        step_wall["e2e"].append(round((time.perf_counter() - ts) * 1e3, 1))
     barrier()
     ev3.record()
     ev3.synchronize()
@@ -322,6 +327,7 @@ def main():
                        "outlier_ratio": 0.3, "wave": args.wave, "fallback": "lazy" if args.lazy else "prefetched",
                        "l2": "inputs (%.1f GB of FP64 correspondences) larger than the 126 MB L2" % (P * n_corr * 32 / 1e9),
                        "parallelism": "pairs sharded over %d rank(s), verdict all-gather" % world},
+            "step_wall_ms": step_wall,
             "e2e": {"value": e2e, "unit": "pairs/s", "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": int(st_e2e["h2d_bytes"] // K), "d2h_bytes_per_step": int(st_e2e["d2h_bytes"] // K)},
             "gpu_launches": int(st["launches"]),

@@ -292,8 +292,7 @@ void aStar(const GraphView &gv, const double *sim /*transposed*/, uint32_t V, ui
             const Adj &e = entryAt(pn.listOwner, top.entry);
             uint32_t next = e.next;
             if (pn.listOwner != pn.vertex) next = e.next == pn.vertex ? pn.listOwner : e.next;
-            double h = simTo[next];
-            h = h < 0.0 ? 0.0 : (1.0 < h ? 1.0 : h);
+            const double h = simTo[next];  // already clamped
             node.vertex = next;
             node.parent = top.parent;
             node.depth = pn.depth + 1;
@@ -345,12 +344,20 @@ void aStar(const GraphView &gv, const double *sim /*transposed*/, uint32_t V, ui
                 if (lv != v) next = e.next == v ? lv : e.next;  // stale list of another vertex (unreachable, see above)
                 if (mark[next] == epoch) return;  // nodeStates.find(next) != end  :855-856
                 const double edgeCost = c0 > e.score ? e.score : c0;  // MIN :843
-                double h = simTo[next];  // getSimilarity(next, to)
-                h = h < 0.0 ? 0.0 : (1.0 < h ? 1.0 : h);  // std::clamp(similarity, 0, 1)  :594
+                const double h = simTo[next];  // std::clamp(getSimilarity(next, to), 0, 1)  :594 (pre-clamped table)
                 const double nextToDest = c1 < h ? h : c1;  // MAX :847
                 const double combined = weight * edgeCost + oneMinusWeight * nextToDest;  // :851-852
-                S.heap.push_back(HeapItem{combined, ni, entry});
-                std::push_heap(S.heap.begin(), S.heap.end(), cmp);
+                // std::push_heap, spelled out (libstdc++ std::__push_heap: sift the hole up while parent < value)
+                S.heap.emplace_back();
+                HeapItem *first = S.heap.data();
+                size_t hole = S.heap.size() - 1;
+                while (hole > 0) {
+                    const size_t parent = (hole - 1) / 2;
+                    if (!(first[parent].f < combined)) break;
+                    first[hole] = first[parent];
+                    hole = parent;
+                }
+                first[hole] = HeapItem{combined, ni, entry};
                 ++out.pushes;
             };
             for (const Adj &e : g.byVertex[lv]) visit(e);
@@ -752,9 +759,13 @@ int32_t pgb_create(const pgb_config *cfg, uint64_t n_views, const double *sim, u
     b->cfg = *cfg;
     if (b->cfg.host_threads <= 0) b->cfg.host_threads = (int32_t)std::max(1u, std::thread::hardware_concurrency());
     b->V = (uint32_t)n_views;
-    b->sim.resize(n_views * n_views);  // stored TRANSPOSED: sim[to * V + next] = similarity(next, to)
+    b->sim.resize(n_views * n_views);  // stored TRANSPOSED and already clamped to [0,1] (std::clamp at graph_traversal.h:594
+                                       // is the only consumer): sim[to * V + next] = clamp(similarity(next, to), 0, 1)
     for (uint64_t r = 0; r < n_views; r++)
-        for (uint64_t c = 0; c < n_views; c++) b->sim[c * n_views + r] = sim[r * n_views + c];
+        for (uint64_t c = 0; c < n_views; c++) {
+            const double v = sim[r * n_views + c];
+            b->sim[c * n_views + r] = v < 0.0 ? 0.0 : (1.0 < v ? 1.0 : v);
+        }
     b->P = n_pairs;
     b->pairViews.assign(pair_views, pair_views + 2 * n_pairs);
     b->mOffset.assign(m_offset, m_offset + n_pairs + 1);

@@ -339,7 +339,7 @@ pgi_status submitWave(pgi_ctx *ctx, const Registration &r, uint32_t n, const uin
             ctx->nChunks = std::min(chunks, kMaxChunks);
             for (int c = 0; c < ctx->nChunks; c++) {
                 const uint32_t threads = n * kFbChunk;
-                k4_fallback_solve<<<(threads + 63) / 64, 64, 0, s>>>(a, c);
+                k4_fallback_solve<<<(threads + 127) / 128, 128, 0, s>>>(a, c);
                 CK(cudaEventRecord(ctx->evChunk[c][0], s));
                 k5_fallback_score<<<n, kCtaThreads, k5Smem, s>>>(a, c, c == ctx->nChunks - 1 ? 1 : 0, smemPts);
                 CK(cudaEventRecord(ctx->evChunk[c][1], s));

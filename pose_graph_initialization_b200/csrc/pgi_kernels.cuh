@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(64) k2_fivept_first_solution(WaveArgs a)
 // The uniform sampler's sequence depends on N only (persistent-pool partial Fisher-Yates driven by
 // cv::RNG(0)), so the samples come from a per-N table built at registration.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64, 6) k4_fallback_solve(WaveArgs a, int chunk)
+__global__ void __launch_bounds__(128, 4) k4_fallback_solve(WaveArgs a, int chunk)
 {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t w = g / kFbChunk, j = g % kFbChunk;
@@ -386,7 +386,14 @@ __global__ void __launch_bounds__(64, 6) k4_fallback_solve(WaveArgs a, int chunk
 // oracle/pgo_fallback.hpp): terms are produced by IEEE FP64 operations, converted to integers once and
 // added with integer arithmetic, so warps/CTAs may reduce in any order (shuffles, shared-memory atomics).
 // ---------------------------------------------------------------------------------------------
-constexpr int kBatch = 16;                    // fallback iterations scored between two decision points of K5
+#ifndef PGI_K5_BATCH
+#define PGI_K5_BATCH 16
+#endif
+#ifndef PGI_K5_SLICES
+#define PGI_K5_SLICES 1
+#endif
+constexpr int kSlices = PGI_K5_SLICES;         // a scoring pass covers 1/kSlices of the pair's points (fixed-point sums: any split is exact)
+constexpr int kBatch = PGI_K5_BATCH;                    // fallback iterations scored between two decision points of K5
 constexpr double kCostOne = 4294967296.0;     // fixed-point MSAC cost of an outlier (2^32)
 constexpr double kLsScale = 1099511627776.0;  // 2^40: fixed-point scale of the normal-equation products
 
@@ -704,6 +711,7 @@ __device__ __forceinline__ void k5Body(const WaveArgs &a, int chunk, int lastChu
     __shared__ unsigned long long sCost[kBatch][10], sLoCost;
     __shared__ uint32_t sInl[kBatch][10], sLoInl, sModels;
     __shared__ int sNextB, sNextPass, sPassStart[kBatch + 1];
+    __shared__ uint8_t sCnt[kFbChunk];  // models per iteration of this chunk (written by K4)
     __shared__ float sMaxB[8], sMaxD[8];
     __shared__ long long sAcc[45];
     __shared__ double sM[81], sV[81], sEls[9], sBestE[9];
@@ -719,9 +727,12 @@ __device__ __forceinline__ void k5Body(const WaveArgs &a, int chunk, int lastChu
         sHave = st.bestCost != ~0ull ? 1 : 0;
         for (int k = 0; k < 9; k++) sBestE[k] = st.bestE[k];
     }
-    if (threadIdx.x < kBatch * 10) { sCost[threadIdx.x / 10][threadIdx.x % 10] = 0; sInl[threadIdx.x / 10][threadIdx.x % 10] = 0; }
+    for (int t = threadIdx.x; t < kBatch * 10; t += kCtaThreads) { sCost[t / 10][t % 10] = 0; sInl[t / 10][t % 10] = 0; }
     if (threadIdx.x == 0) sModels = 0;
+    if (threadIdx.x < kFbChunk) sCnt[threadIdx.x] = a.fbCounts[(size_t)w * kFbChunk + threadIdx.x];
     const bool active = (flags0 & ST_FB_ACTIVE) != 0;
+    const int nSlices = N >= 512u * kSlices ? kSlices : 1;
+    const uint32_t slicePer = ((N + nSlices - 1) / nSlices + 31) & ~31u;
     F32Consts fc{3.0e38f};
     if (USE_F32 && active) {
         float maxB = 0.f, maxD = 0.f;
@@ -765,7 +776,7 @@ __device__ __forceinline__ void k5Body(const WaveArgs &a, int chunk, int lastChu
                 int acc = 0;
                 for (int bI = 0; bI < nb; bI++) {
                     sPassStart[bI] = acc;
-                    acc += (a.fbCounts[(size_t)w * kFbChunk + (it + bI - chunk * kFbChunk)] + 1) / 2;
+                    acc += ((sCnt[it + bI - chunk * kFbChunk] + 1) / 2) * nSlices;
                 }
                 sPassStart[nb] = acc;
                 sNextPass = 0;
@@ -778,22 +789,25 @@ __device__ __forceinline__ void k5Body(const WaveArgs &a, int chunk, int lastChu
                 if (pass >= sPassStart[nb]) break;
                 int bI = 0;
                 while (pass >= sPassStart[bI + 1]) ++bI;
-                const int q = 2 * (pass - sPassStart[bI]);
+                const int rel = pass - sPassStart[bI];
+                const int q = 2 * (rel / nSlices);
+                const uint32_t lo = min((uint32_t)(rel % nSlices) * slicePer, N);
+                const uint32_t hi = min(lo + slicePer, N);
                 const int j = it + bI - chunk * kFbChunk;
-                const int ns = a.fbCounts[(size_t)w * kFbChunk + j];
+                const int ns = sCnt[j];
                 const double *sols = a.fbSols + ((size_t)w * kFbChunk + j) * 90;
                 const float4 *solsF = a.fbSolsF + ((size_t)w * kFbChunk + j) * 30;
                 unsigned long long c[2];
                 uint32_t n[2];
                 const bool two = q + 1 < ns;
-                scoreModelsWarp<USE_F32>(rows, sPts, N, sols + q * 9, two ? sols + (q + 1) * 9 : nullptr, solsF + q * 3, thrSq, truncSq,
-                                         invT, fc.rOut, sQueue, c, n);
+                scoreModelsWarp<USE_F32>(rows + lo, sPts + lo, hi - lo, sols + q * 9, two ? sols + (q + 1) * 9 : nullptr, solsF + q * 3,
+                                         thrSq, truncSq, invT, fc.rOut, sQueue, c, n);
                 if (lane == 0) {
-                    sCost[bI][q] = c[0];
-                    sInl[bI][q] = n[0];
+                    atomicAdd(&sCost[bI][q], c[0]);
+                    atomicAdd(&sInl[bI][q], n[0]);
                     if (two) {
-                        sCost[bI][q + 1] = c[1];
-                        sInl[bI][q + 1] = n[1];
+                        atomicAdd(&sCost[bI][q + 1], c[1]);
+                        atomicAdd(&sInl[bI][q + 1], n[1]);
                     }
                 }
             }
@@ -806,7 +820,7 @@ __device__ __forceinline__ void k5Body(const WaveArgs &a, int chunk, int lastChu
                     int bI = sNextB, upd = 0;
                     for (; bI < nb && it + bI < sMaxIters && !upd; ++bI) {
                         const int j = it + bI - chunk * kFbChunk;
-                        const int ns = a.fbCounts[(size_t)w * kFbChunk + j];
+                        const int ns = sCnt[j];
                         const double *sols = a.fbSols + ((size_t)w * kFbChunk + j) * 90;
                         for (int q = 0; q < ns; q++)
                             if (sCost[bI][q] < sBestCost) {
@@ -874,7 +888,7 @@ __device__ __forceinline__ void k5Body(const WaveArgs &a, int chunk, int lastChu
             // consumed iterations: sNextB (all nb unless maxIters shrank below it + nb)
             it += sNextB;
             __syncthreads();
-            if (threadIdx.x < kBatch * 10) { sCost[threadIdx.x / 10][threadIdx.x % 10] = 0; sInl[threadIdx.x / 10][threadIdx.x % 10] = 0; }
+            for (int t = threadIdx.x; t < kBatch * 10; t += kCtaThreads) { sCost[t / 10][t % 10] = 0; sInl[t / 10][t % 10] = 0; }
             __syncthreads();
             if (sNextB < nb) break;  // maxIters reached inside the batch
         }

@@ -22,4 +22,6 @@ hoff = np.arange(len(ids) + 1, dtype=np.uint32)
 out2 = eng.run_wave(ids, hoff, hyp, flags=WAVE_PATH)
 st = eng.stats()
 print({k: (round(v, 2) if isinstance(v, float) else v) for k, v in st.items()})
+import hashlib
+print("verdict sha", hashlib.sha1(out.tobytes() + out2.tobytes()).hexdigest()[:12])
 print("fallback accepted", int(out["accepted"].sum()), "path accepted", int((out2["branch"] == 1).sum()))
