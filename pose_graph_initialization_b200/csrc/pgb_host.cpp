@@ -261,10 +261,13 @@ void aStar(const GraphView &gv, const double *sim /*transposed*/, uint32_t V, ui
     out.expanded.clear();
     if (S.mark.size() != V) { S.mark.assign(V, 0); S.epoch = 0; }
     if (++S.epoch == 0) { std::fill(S.mark.begin(), S.mark.end(), 0); S.epoch = 1; }
-    S.heap.clear();
     S.arena.clear();
     auto cmp = [](const HeapItem &a, const HeapItem &b) { return a.f < b.f; };  // graph_traversal.h:669-673
-    S.heap.push_back(HeapItem{0.0, UINT32_MAX, 0});  // start node, cost (1,0,0)  :721
+    // the priority queue lives in a raw buffer (S.heap is only its storage; hs is the queue size)
+    if (S.heap.size() < 1024) S.heap.resize(1024);
+    HeapItem *H = S.heap.data();
+    size_t hs = 0;
+    H[hs++] = HeapItem{0.0, UINT32_MAX, 0};  // start node, cost (1,0,0)  :721
     const double oneMinusWeight = 1.0 - weight;
     // `edges` keeps its previous content when a vertex has no list (pose_graph.h:145-146).  Every vertex reached by
     // the search has at least the edge it was reached through, and the source has edges whenever hasLink holds, so
@@ -278,11 +281,11 @@ void aStar(const GraphView &gv, const double *sim /*transposed*/, uint32_t V, ui
         const std::vector<Adj> &real = g.byVertex[lv];
         return idx < real.size() ? real[idx] : gv.ov->byVertex[lv][idx - real.size()].a;
     };
-    while (!S.heap.empty()) {
-        const HeapItem top = S.heap.front();
+    while (hs > 0) {
+        const HeapItem top = H[0];
         ++out.touched;  // :750
-        std::pop_heap(S.heap.begin(), S.heap.end(), cmp);
-        S.heap.pop_back();
+        std::pop_heap(H, H + hs, cmp);
+        --hs;
         // materialise the popped node
         ArenaNode node;
         if (top.parent == UINT32_MAX) {
@@ -336,9 +339,20 @@ void aStar(const GraphView &gv, const double *sim /*transposed*/, uint32_t V, ui
         if (node.depth < maxDepth && listOwner != UINT32_MAX) {  // :820
             const uint32_t lv = listOwner;
             const double c0 = node.c0, c1 = node.c1;
-            uint32_t idx = 0;
-            auto visit = [&](const Adj &e) {
-                const uint32_t entry = idx++;
+            // Children are pushed with std::push_heap semantics, spelled out (libstdc++ std::__push_heap: sift the hole
+            // up while parent < value) on a raw buffer sized for the whole edge list up front.
+            const std::vector<Adj> &rl = g.byVertex[lv];
+            const std::vector<OvAdj> *ol = gv.ov ? &gv.ov->byVertex[lv] : nullptr;
+            const size_t room = hs + rl.size() + (ol ? ol->size() : 0);
+            if (S.heap.size() < room) {
+                S.heap.resize(std::max(room, 2 * S.heap.size()));
+                H = S.heap.data();
+            }
+            HeapItem *const first = H;
+            const size_t hs0 = hs;
+            const double wgt = weight;
+            uint32_t entry = 0;
+            auto push = [&](const Adj &e, uint32_t ent) __attribute__((always_inline)) {
                 if (e.score < 0.0) return;  // kMinimumInlierRatio is `const bool` receiving 0.0 (:613, :839)
                 uint32_t next = e.next;     // (v == dst) ? src : dst  :838-840
                 if (lv != v) next = e.next == v ? lv : e.next;  // stale list of another vertex (unreachable, see above)
@@ -346,26 +360,25 @@ void aStar(const GraphView &gv, const double *sim /*transposed*/, uint32_t V, ui
                 const double edgeCost = c0 > e.score ? e.score : c0;  // MIN :843
                 const double h = simTo[next];  // std::clamp(getSimilarity(next, to), 0, 1)  :594 (pre-clamped table)
                 const double nextToDest = c1 < h ? h : c1;  // MAX :847
-                const double combined = weight * edgeCost + oneMinusWeight * nextToDest;  // :851-852
-                // std::push_heap, spelled out (libstdc++ std::__push_heap: sift the hole up while parent < value)
-                S.heap.emplace_back();
-                HeapItem *first = S.heap.data();
-                size_t hole = S.heap.size() - 1;
+                const double combined = wgt * edgeCost + oneMinusWeight * nextToDest;  // :851-852
+                size_t hole = hs++;
                 while (hole > 0) {
                     const size_t parent = (hole - 1) / 2;
                     if (!(first[parent].f < combined)) break;
                     first[hole] = first[parent];
                     hole = parent;
                 }
-                first[hole] = HeapItem{combined, ni, entry};
-                ++out.pushes;
+                first[hole] = HeapItem{combined, ni, ent};
             };
-            for (const Adj &e : g.byVertex[lv]) visit(e);
-            if (gv.ov)
-                for (const OvAdj &oe : gv.ov->byVertex[lv]) {
+            const Adj *ra = rl.data();
+            const uint32_t nr = (uint32_t)rl.size();
+            for (; entry < nr; ++entry) push(ra[entry], entry);
+            if (ol)
+                for (const OvAdj &oe : *ol) {
                     if (oe.pos >= gv.cutoff) break;
-                    visit(oe.a);
+                    push(oe.a, entry++);
                 }
+            out.pushes += (uint32_t)(hs - hs0);
         }
     }
 }

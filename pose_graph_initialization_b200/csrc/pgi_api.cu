@@ -51,6 +51,7 @@ struct pgi_ctx {
     double *d_hyp = nullptr;
     SlotState *d_state = nullptr;
     uint8_t *d_masks = nullptr, *d_fbCounts = nullptr;
+    uint32_t *d_k3Scratch = nullptr;  // per wave slot: K3 vote totals + arrival ticket (zero between launches)
     uint64_t *d_maskOffset = nullptr;
     pgi_verdict *d_verdicts = nullptr;
     double *d_fbSols = nullptr;
@@ -218,7 +219,8 @@ pgi_status ensureWave(pgi_ctx *ctx, const Registration &r, uint32_t n, uint32_t 
         const uint32_t cap = std::max<uint32_t>(std::max(n, ctx->waveCap), 64);
         cudaFree(ctx->d_pairId); cudaFree(ctx->d_hypOffset); cudaFree(ctx->d_state); cudaFree(ctx->d_bits);
         cudaFree(ctx->d_maskOffset); cudaFree(ctx->d_verdicts); cudaFree(ctx->d_fbSols); cudaFree(ctx->d_fbCounts); cudaFree(ctx->d_fbSolsF);
-        ctx->d_fbSolsF = nullptr;
+        cudaFree(ctx->d_k3Scratch);
+        ctx->d_fbSolsF = nullptr; ctx->d_k3Scratch = nullptr;
         ctx->d_pairId = ctx->d_hypOffset = ctx->d_bits = nullptr; ctx->d_state = nullptr; ctx->d_maskOffset = nullptr;
         ctx->d_verdicts = nullptr; ctx->d_fbSols = nullptr; ctx->d_fbCounts = nullptr;
         ctx->fbScratch = false;
@@ -230,6 +232,8 @@ pgi_status ensureWave(pgi_ctx *ctx, const Registration &r, uint32_t n, uint32_t 
         CK(cudaMalloc((void **)&ctx->d_bits, (size_t)cap * 2 * ctx->bitsStride * 4));
         CK(cudaMalloc((void **)&ctx->d_maskOffset, ((size_t)cap + 1) * 8));
         CK(cudaMalloc((void **)&ctx->d_verdicts, (size_t)cap * sizeof(pgi_verdict)));
+        CK(cudaMalloc((void **)&ctx->d_k3Scratch, (size_t)cap * 8 * 4));
+        CK(cudaMemsetAsync(ctx->d_k3Scratch, 0, (size_t)cap * 8 * 4, ctx->stream));
         ctx->waveCap = cap;
     }
     if ((flags & PGI_WAVE_FALLBACK) && !ctx->fbScratch) {
@@ -316,6 +320,7 @@ pgi_status submitWave(pgi_ctx *ctx, const Registration &r, uint32_t n, const uin
     a.fbMaxIters = ctx->cfg.fallback_max_iters; a.thrMultiplier = ctx->cfg.threshold_multiplier;
     a.thrOverride = thrOverride;
     a.fbSols = ctx->d_fbSols; a.fbSolsF = ctx->d_fbSolsF; a.fbCounts = ctx->d_fbCounts; a.counters = ctx->d_counters;
+    a.k3Scratch = ctx->d_k3Scratch;
 
     CK(cudaEventRecord(ctx->evStart, s));  // kernel-only timing: the wave's small H2D copies are before this event
     k1_score_hypotheses<<<n, kCtaThreads, 0, s>>>(a);
@@ -348,7 +353,9 @@ pgi_status submitWave(pgi_ctx *ctx, const Registration &r, uint32_t n, const uin
             ctx->fbLaunched = true;
         }
         CK(cudaEventRecord(ctx->evFbEnd, s));
-        k3_decompose_vote<<<n, kCtaThreads, 0, s>>>(a);
+        // small waves are latency bound: cover each pair by several point-range CTAs until the grid fills the GPU
+        const uint32_t split = n >= 592u ? 1u : std::min(8u, (592u + n - 1) / n);
+        k3_decompose_vote<<<n * split, kCtaThreads, 0, s>>>(a, split);
         ctx->stats.launches += 1;
     } else {
         CK(cudaEventRecord(ctx->evK2, s));
@@ -458,6 +465,7 @@ pgi_status pgi_destroy(pgi_ctx *ctx)
     cudaFree(ctx->d_pairId); cudaFree(ctx->d_hypOffset); cudaFree(ctx->d_bits); cudaFree(ctx->d_hyp);
     cudaFree(ctx->d_state); cudaFree(ctx->d_masks); cudaFree(ctx->d_fbCounts); cudaFree(ctx->d_maskOffset);
     cudaFree(ctx->d_verdicts); cudaFree(ctx->d_fbSols); cudaFree(ctx->d_fbSolsF); cudaFree(ctx->d_counters);
+    cudaFree(ctx->d_k3Scratch);
     cudaFreeHost(ctx->h_pairId); cudaFreeHost(ctx->h_hypOffset); cudaFreeHost(ctx->h_hyp);
     cudaFreeHost(ctx->h_maskOffset); cudaFreeHost(ctx->h_verdicts); cudaFreeHost(ctx->h_counters);
     cudaEvent_t evs[] = {ctx->evBegin, ctx->evStart, ctx->evK1, ctx->evK2, ctx->evK3, ctx->evFbEnd};

@@ -88,6 +88,7 @@ struct WaveArgs {
     float4 *fbSolsF;    // n x kFbChunk x 10 models x 3 float4 (FP32 copy for the certificate)
     uint8_t *fbCounts;  // n x kFbChunk
     unsigned long long *counters;  // [0] corr evals, [1] fallback pairs, [2] fallback models
+    uint32_t *k3Scratch;  // n x 8: votes[4], arrival ticket of the K3 point-range CTAs (all zero between launches)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -1000,12 +1001,14 @@ __device__ inline void decomposeVoteBlock(const double E[9], const double4 *rows
 // K3 (+K8): E -> (R1,R2,+-t) by the Eigen-faithful 3x3 Jacobi SVD, then the triangulation vote over
 // ALL correspondences: 4 candidates x N 4x4 Jacobi SVDs, register resident, one thread per
 // correspondence (looping the 4 candidates so the strict-< winner logic of pose_utils.h:226-230 is
-// local).  FP64-pipe bound.  Thread 0 picks the first maximum, converts to a unit quaternion and
-// packs the 160-byte verdict.
+// local).  FP64-pipe bound.  A pair is covered by `split` CTAs, each voting over a contiguous range of its
+// points (small waves are latency bound: the host picks split so that the grid fills the GPU); the votes are
+// integer counts, so merging them through global atomics is exact.  The last CTA of a pair to arrive picks the
+// first maximum, converts to a unit quaternion and packs the 160-byte verdict.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kCtaThreads, 2) k3_decompose_vote(WaveArgs a)
+__global__ void __launch_bounds__(kCtaThreads, 2) k3_decompose_vote(WaveArgs a, uint32_t split)
 {
-    const uint32_t w = blockIdx.x;
+    const uint32_t w = blockIdx.x / split, part = blockIdx.x % split;
     if (w >= a.n) return;
     const SlotState &st = a.state[w];
     const uint32_t pid = a.pairId[w];
@@ -1018,7 +1021,20 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k3_decompose_vote(WaveArgs a)
     if (flags & ST_HAVE_E) {
         double E[9];
         for (int k = 0; k < 9; k++) E[k] = st.E[k];
-        decomposeVoteBlock(E, reinterpret_cast<const double4 *>(a.corr) + r0, N, sR, sT, sVotes);
+        const uint32_t per = (N + split - 1) / split;
+        const uint32_t lo = min(part * per, N), hi = min(lo + per, N);
+        decomposeVoteBlock(E, reinterpret_cast<const double4 *>(a.corr) + r0 + lo, hi - lo, sR, sT, sVotes);
+    }
+    if (threadIdx.x == 0 && split > 1) {
+        uint32_t *g = a.k3Scratch + (size_t)w * 8;
+        if (flags & ST_HAVE_E)
+            for (int c = 0; c < 4; c++)
+                if (sVotes[c]) atomicAdd(&g[c], sVotes[c]);
+        __threadfence();
+        if (atomicAdd(&g[4], 1u) != split - 1) return;  // not the last range of this pair
+        __threadfence();
+        for (int c = 0; c < 4; c++) sVotes[c] = atomicExch(&g[c], 0u);  // collect the totals and leave the scratch zeroed
+        atomicExch(&g[4], 0u);
     }
     if (threadIdx.x == 0) {
         pgi_verdict v;
