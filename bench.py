@@ -248,9 +248,12 @@ def main():
     for _ in range(args.steps):
         ts = time.perf_counter()
         pgb.prepare()
+        tp = time.perf_counter()
         graph = pgb.run()
         n_edges = graph.numEdges()
         step_wall["e2e"].append(round((time.perf_counter() - ts) * 1e3, 1))
+        step_wall.setdefault("e2e_detail", []).append(
+            {"prepare_ms": round((tp - ts) * 1e3, 1), **{k: round(v * 1e3, 1) for k, v in pgb.timing.items() if k.endswith("_s")}})
     barrier()
     ev3.record()
     ev3.synchronize()

@@ -51,6 +51,13 @@ struct pgi_ctx {
     double *d_hyp = nullptr;
     SlotState *d_state = nullptr;
     uint8_t *d_masks = nullptr, *d_fbCounts = nullptr;
+    // staging of pgi_register_scene's compact inputs; kept between registrations (cudaMalloc / cudaFree of GB-sized
+    // buffers costs up to hundreds of milliseconds and synchronises the device)
+    double *d_stFocal = nullptr, *d_stSize = nullptr;
+    uint64_t *d_stKpOff = nullptr;
+    float2 *d_stKp = nullptr;
+    uint2 *d_stPv = nullptr, *d_stM = nullptr;
+    size_t capStFocal = 0, capStSize = 0, capStKpOff = 0, capStKp = 0, capStPv = 0, capStM = 0;
     uint32_t *d_k3Scratch = nullptr;  // per wave slot: K3 vote totals + arrival ticket (zero between launches)
     uint64_t *d_maskOffset = nullptr;
     pgi_verdict *d_verdicts = nullptr;
@@ -329,7 +336,12 @@ pgi_status submitWave(pgi_ctx *ctx, const Registration &r, uint32_t n, const uin
     ctx->fbLaunched = false;
     ctx->nChunks = 0;
     if (!scoreOnly) {
-        k2_fivept_first_solution<<<(n + 63) / 64, 64, 0, s>>>(a);
+        // the solve is one long serial chain per pair: on small waves give every pair a warp of its own (no divergence
+        // serialisation between pairs, all SMs used); large waves pack 64 pairs per CTA for throughput
+        if (n <= 4096u)
+            k2_fivept_first_solution<<<n, 32, 0, s>>>(a, 1);
+        else
+            k2_fivept_first_solution<<<(n + 63) / 64, 64, 0, s>>>(a, 0);
         CK(cudaEventRecord(ctx->evK2, s));
         ctx->stats.launches += 1;
         if (flags & PGI_WAVE_FALLBACK) {
@@ -355,7 +367,7 @@ pgi_status submitWave(pgi_ctx *ctx, const Registration &r, uint32_t n, const uin
         CK(cudaEventRecord(ctx->evFbEnd, s));
         // small waves are latency bound: cover each pair by several point-range CTAs until the grid fills the GPU
         const uint32_t split = n >= 592u ? 1u : std::min(8u, (592u + n - 1) / n);
-        k3_decompose_vote<<<n * split, kCtaThreads, 0, s>>>(a, split);
+        k3_decompose_vote<<<n * split, kK3Threads, 0, s>>>(a, split);
         ctx->stats.launches += 1;
     } else {
         CK(cudaEventRecord(ctx->evK2, s));
@@ -466,6 +478,7 @@ pgi_status pgi_destroy(pgi_ctx *ctx)
     cudaFree(ctx->d_state); cudaFree(ctx->d_masks); cudaFree(ctx->d_fbCounts); cudaFree(ctx->d_maskOffset);
     cudaFree(ctx->d_verdicts); cudaFree(ctx->d_fbSols); cudaFree(ctx->d_fbSolsF); cudaFree(ctx->d_counters);
     cudaFree(ctx->d_k3Scratch);
+    cudaFree(ctx->d_stFocal); cudaFree(ctx->d_stSize); cudaFree(ctx->d_stKpOff); cudaFree(ctx->d_stKp); cudaFree(ctx->d_stPv); cudaFree(ctx->d_stM);
     cudaFreeHost(ctx->h_pairId); cudaFreeHost(ctx->h_hypOffset); cudaFreeHost(ctx->h_hyp);
     cudaFreeHost(ctx->h_maskOffset); cudaFreeHost(ctx->h_verdicts); cudaFreeHost(ctx->h_counters);
     cudaEvent_t evs[] = {ctx->evBegin, ctx->evStart, ctx->evK1, ctx->evK2, ctx->evK3, ctx->evFbEnd};
@@ -520,20 +533,20 @@ pgi_status pgi_register_scene(pgi_ctx *ctx, uint64_t n_views, const double *foca
     if ((st = growDevice(ctx, &r.d_corr, r.capRows, (size_t)nRows * 4)) != PGI_OK) return st;
     if ((st = growDevice(ctx, &r.d_offset, r.capOffset, (size_t)n_pairs + 1)) != PGI_OK) return st;
     if ((st = growDevice(ctx, &r.d_thr, r.capThr, (size_t)n_pairs)) != PGI_OK) return st;
-    // staging buffers for the compact inputs (freed after the build kernel)
-    double *d_focal = nullptr, *d_size = nullptr;
-    uint64_t *d_kpOff = nullptr;
-    float2 *d_kp = nullptr;
-    uint2 *d_pv = nullptr, *d_m = nullptr;
+    // staging buffers for the compact inputs (owned by the context, grown on demand)
+    if ((st = growDevice(ctx, &ctx->d_stFocal, ctx->capStFocal, (size_t)n_views)) != PGI_OK) return st;
+    if ((st = growDevice(ctx, &ctx->d_stSize, ctx->capStSize, (size_t)n_views * 2)) != PGI_OK) return st;
+    if ((st = growDevice(ctx, &ctx->d_stKpOff, ctx->capStKpOff, (size_t)n_views + 1)) != PGI_OK) return st;
+    if ((st = growDevice(ctx, &ctx->d_stKp, ctx->capStKp, (size_t)nKp)) != PGI_OK) return st;
+    if ((st = growDevice(ctx, &ctx->d_stPv, ctx->capStPv, (size_t)n_pairs)) != PGI_OK) return st;
+    if ((st = growDevice(ctx, &ctx->d_stM, ctx->capStM, (size_t)nRows)) != PGI_OK) return st;
+    double *d_focal = ctx->d_stFocal, *d_size = ctx->d_stSize;
+    uint64_t *d_kpOff = ctx->d_stKpOff;
+    float2 *d_kp = ctx->d_stKp;
+    uint2 *d_pv = ctx->d_stPv, *d_m = ctx->d_stM;
     cudaStream_t s = ctx->stream;
-    auto cleanup = [&]() { cudaFree(d_focal); cudaFree(d_size); cudaFree(d_kpOff); cudaFree(d_kp); cudaFree(d_pv); cudaFree(d_m); };
+    auto cleanup = [&]() {};
 #define CKC(call) do { cudaError_t e2__ = (call); if (e2__ != cudaSuccess) { cleanup(); ctx->err = std::string(#call) + ": " + cudaGetErrorString(e2__); return e2__ == cudaErrorMemoryAllocation ? PGI_ERR_NOMEM : PGI_ERR_CUDA; } } while (0)
-    CKC(cudaMalloc((void **)&d_focal, std::max<uint64_t>(n_views, 1) * 8));
-    CKC(cudaMalloc((void **)&d_size, std::max<uint64_t>(n_views, 1) * 16));
-    CKC(cudaMalloc((void **)&d_kpOff, (n_views + 1) * 8));
-    CKC(cudaMalloc((void **)&d_kp, std::max<uint64_t>(nKp, 1) * 8));
-    CKC(cudaMalloc((void **)&d_pv, std::max<uint64_t>(n_pairs, 1) * 8));
-    CKC(cudaMalloc((void **)&d_m, std::max<uint64_t>(nRows, 1) * 8));
     CKC(cudaMemcpyAsync(d_focal, focal, n_views * 8, cudaMemcpyHostToDevice, s));
     CKC(cudaMemcpyAsync(d_size, size_wh, n_views * 16, cudaMemcpyHostToDevice, s));
     CKC(cudaMemcpyAsync(d_kpOff, kp_offset, (n_views + 1) * 8, cudaMemcpyHostToDevice, s));

@@ -271,13 +271,15 @@ __device__ inline uint32_t selectRank(const uint32_t *bits, uint32_t nWords, uin
 // ---------------------------------------------------------------------------------------------
 // K2: legacy cv::findEssentialMat(RANSAC, threshold = DBL_MAX) on the inliers of the hypothesis:
 // MWC RNG(2^64-1) draws 5 distinct ranks in [0,k); the first solution of the first sample that yields
-// a model wins and every point is its inlier.  One thread per wave pair.  The Durand-Kerner
+// a model wins and every point is its inlier.  One thread per wave pair (a warp of its own on
+// small waves, where the kernel is a latency chain).  The Durand-Kerner
 // root solve stops at convergence (kLegacyDkTolSq) rather than burning cv::solvePoly's 1000 fixed sweeps — same
 // trajectory, same root order, values equal to cv2's to ~1e-13 (the oracle does the same and is pinned to cv2).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) k2_fivept_first_solution(WaveArgs a)
+__global__ void __launch_bounds__(64) k2_fivept_first_solution(WaveArgs a, int onePairPerWarp)
 {
-    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (onePairPerWarp && threadIdx.x != 0) return;
+    const uint32_t w = onePairPerWarp ? blockIdx.x : blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= a.n) return;
     SlotState &s = a.state[w];
     uint32_t flags = s.flags;
@@ -938,7 +940,10 @@ __device__ __forceinline__ void k5Body(const WaveArgs &a, int chunk, int lastChu
     }
 }
 
-__global__ void __launch_bounds__(kCtaThreads, 3) k5_fallback_score(WaveArgs a, int chunk, int lastChunk, uint32_t smemPts)
+#ifndef PGI_K5_MINB
+#define PGI_K5_MINB 3
+#endif
+__global__ void __launch_bounds__(kCtaThreads, PGI_K5_MINB) k5_fallback_score(WaveArgs a, int chunk, int lastChunk, uint32_t smemPts)
 {
     extern __shared__ float4 sPts[];  // smemPts float4 slots (FP32 copy of the pair's correspondences)
     const uint32_t w = blockIdx.x;
@@ -1006,7 +1011,14 @@ __device__ inline void decomposeVoteBlock(const double E[9], const double4 *rows
 // integer counts, so merging them through global atomics is exact.  The last CTA of a pair to arrive picks the
 // first maximum, converts to a unit quaternion and packs the 160-byte verdict.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kCtaThreads, 2) k3_decompose_vote(WaveArgs a, uint32_t split)
+#ifndef PGI_K3_MINB
+#define PGI_K3_MINB 2
+#endif
+#ifndef PGI_K3_THREADS
+#define PGI_K3_THREADS 256
+#endif
+constexpr int kK3Threads = PGI_K3_THREADS;
+__global__ void __launch_bounds__(kK3Threads, PGI_K3_MINB) k3_decompose_vote(WaveArgs a, uint32_t split)
 {
     const uint32_t w = blockIdx.x / split, part = blockIdx.x % split;
     if (w >= a.n) return;
