@@ -26,7 +26,7 @@ sys.path.insert(0, ROOT)
 
 
 # ncu --set full on k5_fallback_score (profiles/): (dram__bytes_read + dram__bytes_write) / pairs of the launch
-NCU_K5_DRAM_BYTES_PER_PAIR_LAUNCH = 123_000
+NCU_K5_DRAM_BYTES_PER_PAIR_LAUNCH = 164_500
 
 
 def load_peaks():
@@ -295,7 +295,7 @@ def main():
     k5_launches = max(1, K * ((n_local + pgb.fallback_wave - 1) // pgb.fallback_wave) * 8)
     roof_k5 = {"kernel": "k5_fallback_score", "bound": "fp64", "achieved": k5_flops / k5_t / 1e12 if k5_t > 0 else 0.0,
                "peak": fp64_peak, "unit": "TFLOP/s",
-               # dram__bytes_read+write per launch from profiles/ (ncu --set full, 1184 pairs x 125 iterations): ~146 MB;
+               # dram__bytes_read+write per launch from profiles/ (ncu --set full, 1184 pairs x 125 iterations): ~195 MB;
                # algorithmic bytes per launch = pairs x N x 32 B read once
                "traffic": NCU_K5_DRAM_BYTES_PER_PAIR_LAUNCH * min(n_local, pgb.fallback_wave),
                # FP64 rows staged once per CTA + the (72 B FP64 + 48 B FP32) model records of the chunk's iterations

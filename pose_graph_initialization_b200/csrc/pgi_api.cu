@@ -349,9 +349,9 @@ pgi_status submitWave(pgi_ctx *ctx, const Registration &r, uint32_t n, const uin
             // FP32 staging area of K5: the largest pair if it fits, else 0 (those pairs take the FP64-only path)
             uint32_t smemPts = r.maxN <= kK5MaxSmemPts ? std::max<uint32_t>(r.maxN, 1) : kK5MaxSmemPts;
             // + per-warp compaction queues: 8 warps x min(smemPts, 2048) uint16
-            const size_t k5Smem = (size_t)smemPts * 16 + (size_t)8 * (smemPts < 2048u ? ((smemPts + 31u) & ~31u) : 2048u) * 2 +
+            const size_t k5Smem = (size_t)smemPts * 16 + (size_t)8 * (smemPts < kK5QueuePts ? ((smemPts + 31u) & ~31u) : kK5QueuePts) * 2 +
                                   (size_t)((smemPts + 31) / 32) * 4;  // + inlier bit mask of the LO refit
-            if (k5Smem > 48 * 1024)
+            if (k5Smem > 40 * 1024)  // static shared memory (~4 KB) counts towards the 48 KB default limit
                 CK(cudaFuncSetAttribute(k5_fallback_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k5Smem));
             ctx->nChunks = std::min(chunks, kMaxChunks);
             for (int c = 0; c < ctx->nChunks; c++) {

@@ -278,6 +278,7 @@ __device__ inline uint32_t selectRank(const uint32_t *bits, uint32_t nWords, uin
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(64) k2_fivept_first_solution(WaveArgs a, int onePairPerWarp)
 {
+    __shared__ double sWs[kFivePointWs];  // work arrays of the lone lane (onePairPerWarp)
     if (onePairPerWarp && threadIdx.x != 0) return;
     const uint32_t w = onePairPerWarp ? blockIdx.x : blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= a.n) return;
@@ -303,7 +304,8 @@ __global__ void __launch_bounds__(64) k2_fivept_first_solution(WaveArgs a, int o
                 const double4 c = rows[selectRank(bits, nWords, i)];
                 x1[2 * i] = c.x; x1[2 * i + 1] = c.y; x2[2 * i] = c.z; x2[2 * i + 1] = c.w;
             }
-            found = fivePoint<false>(x1, x2, E, 1, 1000, kLegacyDkTolSq) > 0;
+            found = (onePairPerWarp ? fivePoint<false, true>(x1, x2, E, 1, 1000, kLegacyDkTolSq, sWs)
+                                    : fivePoint<false>(x1, x2, E, 1, 1000, kLegacyDkTolSq)) > 0;
         } else {
             CvRng rng((uint64_t)-1);
             for (int iter = 0; iter < 1000 && !found; iter++) {
@@ -320,7 +322,8 @@ __global__ void __launch_bounds__(64) k2_fivept_first_solution(WaveArgs a, int o
                     const double4 c = rows[selectRank(bits, nWords, (uint32_t)idx_i)];
                     x1[2 * i] = c.x; x1[2 * i + 1] = c.y; x2[2 * i] = c.z; x2[2 * i + 1] = c.w;
                 }
-                found = fivePoint<false>(x1, x2, E, 1, 1000, kLegacyDkTolSq) > 0;
+                found = (onePairPerWarp ? fivePoint<false, true>(x1, x2, E, 1, 1000, kLegacyDkTolSq, sWs)
+                                        : fivePoint<false>(x1, x2, E, 1, 1000, kLegacyDkTolSq)) > 0;
             }
         }
         if (!(flags & ST_NEED_5PT)) {
@@ -395,6 +398,10 @@ __global__ void __launch_bounds__(128, 4) k4_fallback_solve(WaveArgs a, int chun
 #ifndef PGI_K5_SLICES
 #define PGI_K5_SLICES 1
 #endif
+#ifndef PGI_K5_QUEUE
+#define PGI_K5_QUEUE 2048
+#endif
+constexpr uint32_t kK5QueuePts = PGI_K5_QUEUE;  // points per scoring block = entries of a warp's compaction queue (<= 2048: 64 mask bits per lane)
 constexpr int kSlices = PGI_K5_SLICES;         // a scoring pass covers 1/kSlices of the pair's points (fixed-point sums: any split is exact)
 constexpr int kBatch = PGI_K5_BATCH;                    // fallback iterations scored between two decision points of K5
 constexpr double kCostOne = 4294967296.0;     // fixed-point MSAC cost of an outlier (2^32)
@@ -480,7 +487,7 @@ __device__ __forceinline__ void scoreModelsWarp(const double4 *rows, const float
                                                 double thrSq, double truncSq, double invT, float rOut, uint16_t *queue /*2048*/,
                                                 unsigned long long costOut[2], uint32_t inlOut[2])
 {
-    // ONE warp scores the model(s) over all N correspondences (lane l: points l, l + 32, ...), in blocks of 2048
+    // ONE warp scores the model(s) over all N correspondences (lane l: points l, l + 32, ...), in blocks of kK5QueuePts
     // points so that a lane's uncertainty mask fits 64 bits.  No cross-warp reduction is needed.
     const uint32_t lane = threadIdx.x & 31;
     unsigned long long cost0 = 0, cost1 = 0;
@@ -490,9 +497,9 @@ __device__ __forceinline__ void scoreModelsWarp(const double4 *rows, const float
         const float4 a0 = Ef[0], a1 = Ef[1], a2 = Ef[2];  // e0..e8 of model 0
         float4 b0 = a0, b1 = a1, b2 = a2;
         if (two) { b0 = Ef[3]; b1 = Ef[4]; b2 = Ef[5]; }
-        for (uint32_t blk = 0; blk < N; blk += 2048) {
+        for (uint32_t blk = 0; blk < N; blk += kK5QueuePts) {
             unsigned long long m0 = 0, m1 = 0;
-            const uint32_t end = N - blk < 2048 ? N - blk : 2048;  // points in this block
+            const uint32_t end = N - blk < kK5QueuePts ? N - blk : kK5QueuePts;  // points in this block
             uint32_t j = 0;
 #pragma unroll 4
             for (uint32_t o = lane; o < end; o += 32, ++j) {
@@ -952,7 +959,7 @@ __global__ void __launch_bounds__(kCtaThreads, PGI_K5_MINB) k5_fallback_score(Wa
     const uint32_t pid = a.pairId[w];
     const uint32_t N = (uint32_t)(a.offset[pid + 1] - a.offset[pid]);
     // dynamic shared memory: smemPts float4 points, then 8 per-warp queues of min(smemPts, 2048) uint16 indices
-    const uint32_t queueStride = smemPts < 2048u ? ((smemPts + 31u) & ~31u) : 2048u;
+    const uint32_t queueStride = smemPts < kK5QueuePts ? ((smemPts + 31u) & ~31u) : kK5QueuePts;
     uint16_t *sQueueAll = reinterpret_cast<uint16_t *>(sPts + smemPts);
     // inlier bit mask of the LO refit: after the queues (staged pairs) or in global scratch-free form for huge pairs
     uint32_t *sInlBits = reinterpret_cast<uint32_t *>(sQueueAll + 8 * (size_t)queueStride);

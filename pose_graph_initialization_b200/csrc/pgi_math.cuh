@@ -491,11 +491,22 @@ __device__ inline void pmulz(const double *a, int la, const double *b, int lb, d
 // EMEstimatorCallback::runKernel for exactly 5 points.  Writes up to maxOut (<=10) row-major unit-norm
 // essential matrices to Eout and returns the TOTAL number of solutions found (<= 10) when maxOut == 10,
 // or min(total, maxOut) when the caller only needs the first ones.
-template <bool CYCLE_JUMP>
+// EXT_WS: the large work arrays (kFivePointWs doubles) live in caller-provided memory — shared memory when one warp
+// lane solves alone (K2 on small waves): a lone lane's local memory is spread over 32-lane-interleaved lines and
+// thrashes L1, shared memory does not.  Same operations on the same operands either way.
+constexpr int kFivePointWs = 81 + 200 + 100 + 100 + 39 + 60;
+template <bool CYCLE_JUMP, bool EXT_WS = false>
 __device__ inline int fivePoint(const double x1[10], const double x2[10], double *Eout, int maxOut, int dkMaxIters,
-                                double dkTolSq)
+                                double dkTolSq, double *ws = nullptr)
 {
-    double Vt[81];
+    double VtL[EXT_WS ? 1 : 81], AL[EXT_WS ? 1 : 200], A1L[EXT_WS ? 1 : 100], invL[EXT_WS ? 1 : 100], bL[EXT_WS ? 1 : 39],
+        R6L[EXT_WS ? 1 : 60];
+    double *const Vt = EXT_WS ? ws : VtL;
+    double *const A = EXT_WS ? ws + 81 : AL;
+    double *const A1 = EXT_WS ? ws + 281 : A1L;
+    double *const inv = EXT_WS ? ws + 381 : invL;
+    double *const b = EXT_WS ? ws + 481 : bL;
+    double *const R6 = EXT_WS ? ws + 520 : R6L;  // rows 4..9 of inv*A2
     for (int i = 0; i < 81; i++) Vt[i] = 0.0;
     for (int i = 0; i < 5; i++) {
         const double a = x1[2 * i], b = x1[2 * i + 1], c = x2[2 * i], d = x2[2 * i + 1];
@@ -506,17 +517,13 @@ __device__ inline int fivePoint(const double x1[10], const double x2[10], double
     cvJacobiSVD<9, 5, 9, false>(Vt, W, nullptr);
     const double *EE = Vt + 45;
 
-    double A[200];
     buildConstraints(EE, A);
 
     // A1 = A[:,0:10], A2 = A[:,10:20]; R = inv(A1) * A2 (rows 4..9 are the ones consumed)
-    double A1[100], inv[100];
     for (int i = 0; i < 10; i++)
         for (int j = 0; j < 10; j++) A1[i * 10 + j] = A[i * 20 + j];
     cvInvert10(A1, inv);
-    double b[39];
     {
-        double R6[60];  // rows 4..9 of inv*A2
         for (int i = 0; i < 6; i++)
             for (int j = 0; j < 10; j++) {
                 double s = 0;
