@@ -89,6 +89,11 @@ def make_scene(name):
     return S.make_scene(**S.CONFIGS[name])
 
 
+def scene_outlier_ratio(name):
+    from pose_graph_initialization_b200 import scene as S
+    return S.CONFIGS.get(name, {}).get("outlier_ratio")
+
+
 def dense_sample(scene, pair_ids, thr_px=0.4):
     from pose_graph_initialization_b200 import scene as S
     corr, thr, off = [], [], [0]
@@ -327,7 +332,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_resident / K, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.config, "views": int(len(scene["focal"])), "pairs": int(P), "corr_per_pair": n_corr,
-                       "outlier_ratio": 0.3, "wave": args.wave, "fallback": "lazy" if args.lazy else "prefetched",
+                       "outlier_ratio": scene_outlier_ratio(args.config), "wave": args.wave, "fallback": "lazy" if args.lazy else "prefetched",
                        "l2": "inputs (%.1f GB of FP64 correspondences) larger than the 126 MB L2" % (P * n_corr * 32 / 1e9),
                        "parallelism": "pairs sharded over %d rank(s), verdict all-gather" % world},
             "step_wall_ms": step_wall,
