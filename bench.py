@@ -174,6 +174,8 @@ def main():
     ap.add_argument("--window", type=int, default=0, help="host re-search window (0 = library default)")
     ap.add_argument("--no-overlap", action="store_true", help="prefetch the fallback before the waves instead of concurrently")
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the cpu_baseline sample (0 = 256 x cores, ~10-15 s)")
+    ap.add_argument("--fb-wave", type=int, default=1024, help="pairs per fallback prefetch wave")
+    ap.add_argument("--fb-streams", type=int, default=2, help="background contexts running prefetch waves concurrently")
     ap.add_argument("--lazy", action="store_true", help="run the fallback lazily inside the waves instead of prefetching it")
     args = ap.parse_args()
 
@@ -213,7 +215,7 @@ def main():
     n_corr = int(scene["m_offset"][1] - scene["m_offset"][0])
     pgb = B.PoseGraphBuilder(kCoreNumber_=max(1, (os.cpu_count() or 1) // world),  # ranks share the box's cores
                               kSimilarityThreshold_=0.0, scene=scene, device=local_rank,
-                             wave_size=args.wave, prefetch_fallback=not args.lazy, overlap_fallback=not args.no_overlap, research_window=args.window, group=group, rank=rank,
+                             wave_size=args.wave, prefetch_fallback=not args.lazy, overlap_fallback=not args.no_overlap, research_window=args.window, fallback_wave=args.fb_wave, prefetch_streams=args.fb_streams, group=group, rank=rank,
                              world_size=world)
     pgb.prepare()
     fp64_peak = pgb.engine.fp64_peak(fused=False)

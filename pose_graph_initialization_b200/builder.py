@@ -280,7 +280,8 @@ class PoseGraphBuilder:
                  kTraversalHeuristicsWeight_=0.8, kSimilarityThreshold_=0.5, kInlierOutlierThreshold_=0.4,
                  kImagePath_="", kWorkspacePath_="", kSimilarityGraphPath_="", kFocalLengthPath_="",
                  kUsePathFinding_=True, kUseGPU_=True, kUseEpipolarHashing_=False, *, scene=None, device=0,
-                 wave_size=1024, prefetch_fallback=True, fallback_wave=2048, overlap_fallback=True, research_window=0,
+                 wave_size=1024, prefetch_fallback=True, fallback_wave=1024, overlap_fallback=True, research_window=0,
+                 prefetch_streams=2,
                  group=None, rank=0, world_size=1):
         if not kUseGPU_:
             raise ValueError("the B200 path has no CPU implementation (kUseGPU_ must be true)")
@@ -307,6 +308,8 @@ class PoseGraphBuilder:
         self.pf_group = None
         self.engine = None
         self.engine_fb = None
+        self.engine_fb2 = None
+        self.prefetch_streams = int(prefetch_streams)
         self.timing = {}
 
     # -- engine + registration (H2D inside, counted by the engine's stats) -----------------------------------
@@ -320,27 +323,34 @@ class PoseGraphBuilder:
             if self.engine_fb is None:
                 self.engine_fb = _engine.Engine(device=self.device, min_inliers=self.min_inliers, background=True)
             self.engine_fb.share_pairs(self.engine)
+            if self.prefetch_streams > 1:
+                # a second background context: its K4/K5 launches fill the tail waves of the first one's
+                if self.engine_fb2 is None:
+                    self.engine_fb2 = _engine.Engine(device=self.device, min_inliers=self.min_inliers, background=True)
+                self.engine_fb2.share_pairs(self.engine)
             if self.world > 1 and self.pf_group is None:
                 import torch.distributed as dist
                 self.pf_group = dist.new_group(backend="gloo")
 
     def engine_stats(self):
         st = self.engine.stats()
-        if self.engine_fb is not None:
-            for k, v in self.engine_fb.stats().items():
-                st[k] += v
+        for e in (self.engine_fb, self.engine_fb2):
+            if e is not None:
+                for k, v in e.stats().items():
+                    st[k] += v
         return st
 
     def reset_engine_stats(self):
         self.engine.reset_stats()
-        if self.engine_fb is not None:
-            self.engine_fb.reset_stats()
+        for e in (self.engine_fb, self.engine_fb2):
+            if e is not None:
+                e.reset_stats()
 
     def close(self):
-        for e in (self.engine_fb, self.engine):
+        for e in (self.engine_fb2, self.engine_fb, self.engine):
             if e is not None:
                 e.close()
-        self.engine = self.engine_fb = None
+        self.engine = self.engine_fb = self.engine_fb2 = None
 
     def _exchange(self, local, counts):
         if self.world == 1:
@@ -387,13 +397,12 @@ class PoseGraphBuilder:
             def prefetch_worker():
                 try:
                     chunk = self.fallback_wave * self.world
-                    for s in range(0, Q, chunk):
-                        ids = queue[s:s + chunk]
-                        ids = ids[ids != np.uint32(0xFFFFFFFF)]
-                        own = owner_of(ids, self.world)
-                        mine = ids[own == self.rank]
-                        v = (self.engine_fb.run_wave(local_id(mine, self.world), None, None, flags=WAVE_FALLBACK)
-                             if len(mine) else np.zeros(0, dtype=VERDICT_DTYPE))
+                    engines = [e for e in (self.engine_fb, self.engine_fb2) if e is not None]
+                    pending = []  # submitted chunks, oldest first: one in flight per background engine
+
+                    def finish(job):
+                        eng, s, ids, own, mine = job
+                        v = eng.wait_wave() if len(mine) else np.zeros(0, dtype=VERDICT_DTYPE)
                         v["pair_id"] = mine.astype(np.uint32)
                         if self.world > 1:  # every rank needs every pair's fallback verdict (predictions + commit)
                             counts = [int(np.count_nonzero(own == r)) for r in range(self.world)]
@@ -406,6 +415,20 @@ class PoseGraphBuilder:
                             host.set_fallback_verdicts_some(ids, v)
                             state["done_pos"] = min(Q, s + chunk)
                             progress.notify_all()
+
+                    for k, s in enumerate(range(0, Q, chunk)):
+                        ids = queue[s:s + chunk]
+                        ids = ids[ids != np.uint32(0xFFFFFFFF)]
+                        own = owner_of(ids, self.world)
+                        mine = ids[own == self.rank]
+                        eng = engines[k % len(engines)]
+                        if len(pending) == len(engines):
+                            finish(pending.pop(0))
+                        if len(mine):
+                            eng.submit_wave(local_id(mine, self.world), None, None, flags=WAVE_FALLBACK)
+                        pending.append((eng, s, ids, own, mine))
+                    while pending:
+                        finish(pending.pop(0))
                 except Exception as exc:  # surface engine failures in the main thread
                     with progress:
                         state["error"] = exc
