@@ -290,6 +290,17 @@ def main():
     k1_pass()
     st_k1 = eng.stats()
 
+    # ---- K5/K4 on one fallback wave with nothing else on the GPU: in the step three contexts overlap (wave loop + two
+    # prefetch streams), so the per-stage CUDA-event brackets there contain each other's kernels; the roofline's launch
+    # durations are taken from this isolated wave of the same pairs instead (same launches: 8 x (K4, K5) + K3).
+    # (1776 pairs = 4 x 148 SMs x 3 resident K5 CTAs: the grid is a whole number of resident waves, as the two prefetch
+    # streams of the step fill each other's partial waves)
+    fb_ids = np.arange(min(n_local, 1776), dtype=np.uint32)
+    eng.run_wave(fb_ids, None, None, flags=B.WAVE_FALLBACK)
+    eng.reset_stats()
+    eng.run_wave(fb_ids, None, None, flags=B.WAVE_FALLBACK)
+    st_fb = eng.stats()
+
     # ---- roofline of the dominant kernel (per-stage CUDA-event times from the engine's own stream) -----------
     stages = {"k1_score_hypotheses": st["ms_score"], "k2_fivept_first_solution": st["ms_fivept"],
               "k4_fallback_solve": st["ms_fallback_solve"], "k5_fallback_score": st["ms_fallback_score"],
@@ -297,18 +308,20 @@ def main():
     dominant = max(stages, key=stages.get)
     hbm_peak, hbm_src = load_peaks()
     # K5: every scored model evaluates the Sampson residual of all N correspondences: 33 FP64 flops each (algorithmic)
-    k5_flops = st["fallback_models"] * n_corr * 33.0
-    k5_t = st["ms_fallback_score"] * 1e-3
-    k5_launches = max(1, K * ((n_local + pgb.fallback_wave - 1) // pgb.fallback_wave) * 8)
+    k5_flops = st_fb["fallback_models"] * n_corr * 33.0
+    k5_t = st_fb["ms_fallback_score"] * 1e-3
+    k5_launches = 8
     roof_k5 = {"kernel": "k5_fallback_score", "bound": "fp64", "achieved": k5_flops / k5_t / 1e12 if k5_t > 0 else 0.0,
                "peak": fp64_peak, "unit": "TFLOP/s",
                # dram__bytes_read+write per launch from profiles/ (ncu --set full, 1184 pairs x 125 iterations): ~195 MB;
                # algorithmic bytes per launch = pairs x N x 32 B read once
-               "traffic": NCU_K5_DRAM_BYTES_PER_PAIR_LAUNCH * min(n_local, pgb.fallback_wave),
+               "traffic": NCU_K5_DRAM_BYTES_PER_PAIR_LAUNCH * len(fb_ids),
                # FP64 rows staged once per CTA + the (72 B FP64 + 48 B FP32) model records of the chunk's iterations
-               "algorithmic_bytes_per_launch": int(min(n_local, pgb.fallback_wave) * (
-                   n_corr * 32 + 120.0 * st["fallback_models"] / max(1, st["fallback_pairs"] * 8))),
-               "launches": k5_launches,
+               "algorithmic_bytes_per_launch": int(len(fb_ids) * (
+                   n_corr * 32 + 120.0 * st_fb["fallback_models"] / max(1, st_fb["fallback_pairs"] * 8))),
+               "launches": k5_launches, "ms_per_launch": st_fb["ms_fallback_score"] / k5_launches,
+               "timed_on": "one isolated %d-pair fallback wave after the timed region (in the step three contexts overlap and "
+                           "their CUDA-event brackets contain each other's kernels)" % len(fb_ids),
                "peak_source": "measured live: DMUL+DADD chains (parity forbids FMA); DFMA peak %.1f TFLOP/s; "
                               "achieved counts 33 algorithmic FP64 flops per model x correspondence evaluation, most of "
                               "which are certified in FP32 (see DESIGN.md section 3)" % fp64_peak_fma}
@@ -345,6 +358,11 @@ def main():
                                     "fallback_models": st["fallback_models"] * n_corr / (ms_resident * 1e-3) / 1e9},
             "roofline": roofline, "roofline_k1_scoring": roof_k1, "roofline_k5_fallback": roof_k5,
             "gpu_stage_ms_per_step": {k: v / K for k, v in stages.items()},
+            "gpu_stage_ms_note": "CUDA-event brackets per context; with the prefetch overlapping the waves the brackets of "
+                                 "concurrent contexts include each other's kernels (sums exceed the step's GPU time)",
+            "gpu_stage_ms_isolated_fallback_wave": {"pairs": int(len(fb_ids)), "k4_fallback_solve": st_fb["ms_fallback_solve"],
+                                                    "k5_fallback_score": st_fb["ms_fallback_score"],
+                                                    "k3_decompose_vote": st_fb["ms_decompose"]},
             "host_s_per_step": {k: timing.get(k) for k in ("prefetch_s", "waves_s", "total_s", "engine_s", "exchange_s", "host_s",
                                                             "wait_prefetch_s", "engine_rounds", "exchanges")},
             "host_counters": counters, "edges": int(n_edges), "wall_s_resident": wall,
