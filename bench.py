@@ -120,6 +120,54 @@ def cpu_leg(scene, n_pairs, threads=0, seed=0):
                 corr=int(off[-1]))
 
 
+def _cv2_usac_one(job):
+    import cv2
+    cv2.setNumThreads(1)
+    c, thr = job
+    E, mask = cv2.findEssentialMat(c[:, :2].copy(), c[:, 2:].copy(), np.eye(3), cv2.USAC_MAGSAC, 0.99, thr)
+    return 0 if mask is None else int(mask.sum())
+
+
+def cv2_yardstick(scene, n_pairs, workers):
+    """Third-party yard-stick of SURVEY 8(d): the fallback call site's own library call, cv2.findEssentialMat(USAC_MAGSAC)
+    from the cv2 wheel of this image, over a process pool of `workers` (fallback stage only: no E->(R,t) vote, no A*).
+    Runs in a fresh child process (this one holds CUDA/NCCL threads) with a hard timeout; None if unavailable."""
+    import tempfile
+    from pose_graph_initialization_b200 import scene as S
+    P = len(scene["pair_views"])
+    ids = np.unique(np.linspace(0, P - 1, n_pairs).astype(np.int64))
+    jobs = [S.pair_correspondences(scene, int(p), 0.4) for p in ids]
+    try:
+        with tempfile.TemporaryDirectory() as tmp:
+            path = os.path.join(tmp, "jobs.npz")
+            np.savez(path, corr=np.stack([c for c, _ in jobs]) if len({len(c) for c, _ in jobs}) == 1 else
+                     np.array([c for c, _ in jobs], dtype=object), thr=np.array([t for _, t in jobs]))
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cv2-yardstick", path, "--workers", str(workers)],
+                               capture_output=True, text=True, timeout=240)
+        return json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 and r.stdout.strip() else None
+    except Exception:
+        return None
+
+
+def cv2_yardstick_child(path, workers):
+    import multiprocessing as mp
+    try:
+        import cv2
+    except Exception:
+        return 1
+    d = np.load(path, allow_pickle=True)
+    jobs = [(np.asarray(c, dtype=np.float64), float(t)) for c, t in zip(d["corr"], d["thr"])]
+    with mp.get_context("fork").Pool(workers) as pool:
+        pool.map(_cv2_usac_one, jobs[:workers])  # warm the workers
+        t0 = time.perf_counter()
+        inl = pool.map(_cv2_usac_one, jobs)
+        dt = time.perf_counter() - t0
+    emit({"pairs_per_s": len(jobs) / dt, "workers": workers, "pairs": len(jobs),
+          "accepted": int(sum(1 for k in inl if k >= 20)),
+          "what": "cv2 %s findEssentialMat(USAC_MAGSAC) only, process pool" % cv2.__version__})
+    return 0
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU path (oracle port: the reference cannot be compiled in this image)
     timed on the host cores.  Rank 0 only."""
@@ -176,8 +224,12 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the cpu_baseline sample (0 = 256 x cores, ~10-15 s)")
     ap.add_argument("--fb-wave", type=int, default=1024, help="pairs per fallback prefetch wave")
     ap.add_argument("--fb-streams", type=int, default=2, help="background contexts running prefetch waves concurrently")
+    ap.add_argument("--cv2-yardstick", default="", help=argparse.SUPPRESS)
+    ap.add_argument("--workers", type=int, default=1, help=argparse.SUPPRESS)
     ap.add_argument("--lazy", action="store_true", help="run the fallback lazily inside the waves instead of prefetching it")
     args = ap.parse_args()
+    if args.cv2_yardstick:  # child mode of cv2_yardstick(): no torch, no CUDA
+        sys.exit(cv2_yardstick_child(args.cv2_yardstick, args.workers))
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -298,8 +350,12 @@ def main():
     fb_ids = np.arange(min(n_local, 1776), dtype=np.uint32)
     eng.run_wave(fb_ids, None, None, flags=B.WAVE_FALLBACK)
     eng.reset_stats()
-    eng.run_wave(fb_ids, None, None, flags=B.WAVE_FALLBACK)
+    v_fb = eng.run_wave(fb_ids, None, None, flags=B.WAVE_FALLBACK)
     st_fb = eng.stats()
+    it = np.sort(v_fb["iters"].astype(np.int64))  # iterations of the robust loop per pair (report next to the rate)
+    fb_iters = {"pairs": int(len(it)), "mean": float(it.mean()), "p10": int(it[len(it) // 10]), "median": int(it[len(it) // 2]),
+                "p90": int(it[(len(it) * 9) // 10]), "max": int(it[-1]),
+                "models_per_pair": st_fb["fallback_models"] / max(1, st_fb["fallback_pairs"])}
 
     # ---- roofline of the dominant kernel (per-stage CUDA-event times from the engine's own stream) -----------
     stages = {"k1_score_hypotheses": st["ms_score"], "k2_fivept_first_solution": st["ms_fivept"],
@@ -342,6 +398,7 @@ def main():
     if rank == 0:
         cores = os.cpu_count() or 1
         cpu = cpu_leg(scene, args.cpu_sample or 256 * cores)  # ~10-15 s of all-core CPU work
+        yard = cv2_yardstick(scene, 8 * cores, cores)  # ~1-2 s
         line = {
             "metric": "image_pairs_verified_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_resident / K, "higher_is_better": True, "scaling": "strong",
@@ -368,7 +425,9 @@ def main():
             "host_counters": counters, "edges": int(n_edges), "wall_s_resident": wall,
             "cpu_baseline": {"value": cpu["pairs_per_s"], "unit": "pairs/s", "cores": cpu["cores"], "kind": "port",
                              "sample": "%d evenly spaced pairs of the same scene through the oracle's estimatePose "
-                                       "(fallback + E->(R,t) vote), %.1f s" % (cpu["pairs"], cpu["seconds"])},
+                                       "(fallback + E->(R,t) vote), %.1f s" % (cpu["pairs"], cpu["seconds"]),
+                             "third_party_yardstick": yard},
+            "fallback_iterations": fb_iters,
             "clocks": clocks,
         }
         emit(line)
