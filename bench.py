@@ -218,7 +218,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--config", default="cfg2_300v")
-    ap.add_argument("--wave", type=int, default=1024)
+    ap.add_argument("--wave", type=int, default=0, help="queue positions per speculative wave (0 = 256 on one GPU, 512 with several ranks: every round of a wave costs a record exchange there)")
     ap.add_argument("--window", type=int, default=0, help="host re-search window (0 = library default)")
     ap.add_argument("--no-overlap", action="store_true", help="prefetch the fallback before the waves instead of concurrently")
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the cpu_baseline sample (0 = 256 x cores, ~10-15 s)")
@@ -233,6 +233,8 @@ def main():
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.wave <= 0:
+        args.wave = 256 if world == 1 else 512
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)

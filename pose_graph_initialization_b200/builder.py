@@ -252,6 +252,33 @@ def allreduce_records(records, group=None, device=None):
     return t.cpu().numpy().view(RECORD_DTYPE)
 
 
+class RecordExchanger:
+    """allreduce_records on a GPU with persistent pinned staging buffers and a persistent device buffer: the exchange
+    is a ~100 KB latency-bound message once per wave round, so the allocations and pageable copies are what it costs."""
+
+    def __init__(self, max_records, device, group=None):
+        import torch
+        self.torch, self.group = torch, group
+        n = int(max_records) * RECORD_DTYPE.itemsize
+        self.pin_in = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        self.pin_out = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        self.dev = torch.empty(n, dtype=torch.uint8, device=device)
+        self.np_in, self.np_out = self.pin_in.numpy(), self.pin_out.numpy()
+
+    def __call__(self, records):
+        import torch.distributed as dist
+        n = records.nbytes
+        if n > self.dev.numel():
+            raise ValueError("record buffer larger than the exchanger's capacity")
+        self.np_in[:n] = records.view(np.uint8).reshape(-1)
+        d = self.dev[:n]
+        d.copy_(self.pin_in[:n], non_blocking=True)
+        dist.all_reduce(d, op=dist.ReduceOp.SUM, group=self.group)
+        self.pin_out[:n].copy_(d, non_blocking=True)
+        self.torch.cuda.current_stream().synchronize()
+        return self.np_out[:n].copy().view(RECORD_DTYPE)
+
+
 class PoseGraph:
     """Result container: committed edges in commit order (pose_graph.h:62-106)."""
 
@@ -280,7 +307,7 @@ class PoseGraphBuilder:
                  kTraversalHeuristicsWeight_=0.8, kSimilarityThreshold_=0.5, kInlierOutlierThreshold_=0.4,
                  kImagePath_="", kWorkspacePath_="", kSimilarityGraphPath_="", kFocalLengthPath_="",
                  kUsePathFinding_=True, kUseGPU_=True, kUseEpipolarHashing_=False, *, scene=None, device=0,
-                 wave_size=1024, prefetch_fallback=True, fallback_wave=1024, overlap_fallback=True, research_window=0,
+                 wave_size=None, prefetch_fallback=True, fallback_wave=1024, overlap_fallback=True, research_window=0,
                  prefetch_streams=2,
                  group=None, rank=0, world_size=1):
         if not kUseGPU_:
@@ -297,7 +324,9 @@ class PoseGraphBuilder:
         self.thr_px = kInlierOutlierThreshold_
         self.min_inliers = kMinimumInlierNumber_
         self.device = device
-        self.wave_size = wave_size
+        # measured on cfg2 (scripts/gpu_sweep.sh): 256 positions per wave is the optimum on one GPU (fewer A* re-searches
+        # per position, rounds are cheap); with several ranks every round also costs a record exchange
+        self.wave_size = wave_size if wave_size else (256 if world_size == 1 else 512)
         self.prefetch_fallback = prefetch_fallback
         self.fallback_wave = fallback_wave
         self.group, self.rank, self.world = group, rank, world_size
@@ -309,6 +338,7 @@ class PoseGraphBuilder:
         self.engine = None
         self.engine_fb = None
         self.engine_fb2 = None
+        self._exchanger = None
         self.prefetch_streams = int(prefetch_streams)
         self.timing = {}
 
@@ -483,7 +513,12 @@ class PoseGraphBuilder:
                         host.commit_wave(verdicts)
                     prof["host_s"] += time.perf_counter() - t_b
                 else:  # WAVE_NEED_EXCHANGE
-                    merged = allreduce_records(host.export_records(), self.group, dev)
+                    if dev is not None:
+                        if self._exchanger is None:
+                            self._exchanger = RecordExchanger(max(self.wave_size, 4096), dev, self.group)
+                        merged = self._exchanger(host.export_records())
+                    else:
+                        merged = allreduce_records(host.export_records(), self.group, dev)
                     t_b = time.perf_counter()
                     prof["exchange_s"] += t_b - t_a
                     prof["exchanges"] += 1
