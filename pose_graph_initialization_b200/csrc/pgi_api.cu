@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -58,6 +59,8 @@ struct pgi_ctx {
     float2 *d_stKp = nullptr;
     uint2 *d_stPv = nullptr, *d_stM = nullptr;
     size_t capStFocal = 0, capStSize = 0, capStKpOff = 0, capStKp = 0, capStPv = 0, capStM = 0;
+    uint32_t *d_dkList = nullptr, *d_dkCtl = nullptr;  // work list of the split K4 (K4a -> K4b -> K4c)
+    bool k4Split = false;  // PGI_K4_SPLIT=1 selects the three-kernel K4 (K4a/K4b/K4c)
     uint32_t *d_k3Scratch = nullptr;  // per wave slot: K3 vote totals + arrival ticket (zero between launches)
     uint64_t *d_maskOffset = nullptr;
     pgi_verdict *d_verdicts = nullptr;
@@ -226,8 +229,8 @@ pgi_status ensureWave(pgi_ctx *ctx, const Registration &r, uint32_t n, uint32_t 
         const uint32_t cap = std::max<uint32_t>(std::max(n, ctx->waveCap), 64);
         cudaFree(ctx->d_pairId); cudaFree(ctx->d_hypOffset); cudaFree(ctx->d_state); cudaFree(ctx->d_bits);
         cudaFree(ctx->d_maskOffset); cudaFree(ctx->d_verdicts); cudaFree(ctx->d_fbSols); cudaFree(ctx->d_fbCounts); cudaFree(ctx->d_fbSolsF);
-        cudaFree(ctx->d_k3Scratch);
-        ctx->d_fbSolsF = nullptr; ctx->d_k3Scratch = nullptr;
+        cudaFree(ctx->d_k3Scratch); cudaFree(ctx->d_dkList);
+        ctx->d_fbSolsF = nullptr; ctx->d_k3Scratch = nullptr; ctx->d_dkList = nullptr;
         ctx->d_pairId = ctx->d_hypOffset = ctx->d_bits = nullptr; ctx->d_state = nullptr; ctx->d_maskOffset = nullptr;
         ctx->d_verdicts = nullptr; ctx->d_fbSols = nullptr; ctx->d_fbCounts = nullptr;
         ctx->fbScratch = false;
@@ -247,6 +250,8 @@ pgi_status ensureWave(pgi_ctx *ctx, const Registration &r, uint32_t n, uint32_t 
         CK(cudaMalloc((void **)&ctx->d_fbSols, (size_t)ctx->waveCap * kFbChunk * 90 * 8));
         CK(cudaMalloc((void **)&ctx->d_fbCounts, (size_t)ctx->waveCap * kFbChunk));
         CK(cudaMalloc((void **)&ctx->d_fbSolsF, (size_t)ctx->waveCap * kFbChunk * 30 * sizeof(float4)));
+        CK(cudaMalloc((void **)&ctx->d_dkList, (size_t)ctx->waveCap * kFbChunk * 4));
+        if (!ctx->d_dkCtl) CK(cudaMalloc((void **)&ctx->d_dkCtl, 2 * 4));
         ctx->fbScratch = true;
     }
     if (nHyp > ctx->hypCap) {
@@ -327,7 +332,7 @@ pgi_status submitWave(pgi_ctx *ctx, const Registration &r, uint32_t n, const uin
     a.fbMaxIters = ctx->cfg.fallback_max_iters; a.thrMultiplier = ctx->cfg.threshold_multiplier;
     a.thrOverride = thrOverride;
     a.fbSols = ctx->d_fbSols; a.fbSolsF = ctx->d_fbSolsF; a.fbCounts = ctx->d_fbCounts; a.counters = ctx->d_counters;
-    a.k3Scratch = ctx->d_k3Scratch;
+    a.k3Scratch = ctx->d_k3Scratch; a.dkList = ctx->d_dkList; a.dkCtl = ctx->d_dkCtl;
 
     CK(cudaEventRecord(ctx->evStart, s));  // kernel-only timing: the wave's small H2D copies are before this event
     k1_score_hypotheses<<<n, kCtaThreads, 0, s>>>(a);
@@ -356,7 +361,14 @@ pgi_status submitWave(pgi_ctx *ctx, const Registration &r, uint32_t n, const uin
             ctx->nChunks = std::min(chunks, kMaxChunks);
             for (int c = 0; c < ctx->nChunks; c++) {
                 const uint32_t threads = n * kFbChunk;
-                k4_fallback_solve<<<(threads + 127) / 128, 128, 0, s>>>(a, c);
+                if (ctx->k4Split) {
+                    CK(cudaMemsetAsync(ctx->d_dkCtl, 0, 8, s));
+                    k4a_polynomial<<<(threads + 127) / 128, 128, 0, s>>>(a, c);
+                    k4b_roots<<<std::min<uint32_t>((threads + 127) / 128, 148u * 4u), 128, 0, s>>>(a);
+                    k4c_solutions<<<(threads + 127) / 128, 128, 0, s>>>(a, c);
+                    ctx->stats.launches += 2;
+                } else
+                    k4_fallback_solve<<<(threads + 127) / 128, 128, 0, s>>>(a, c);
                 CK(cudaEventRecord(ctx->evChunk[c][0], s));
                 k5_fallback_score<<<n, kCtaThreads, k5Smem, s>>>(a, c, c == ctx->nChunks - 1 ? 1 : 0, smemPts);
                 CK(cudaEventRecord(ctx->evChunk[c][1], s));
@@ -436,6 +448,7 @@ pgi_status pgi_create(const pgi_config *cfg, pgi_ctx **out)
     if (prop.major != 10) return PGI_ERR_CUDA;  // kernels are sm_100a-only; there is no other path
     pgi_ctx *ctx = new pgi_ctx();
     ctx->cfg = *cfg;
+    if (const char *e = getenv("PGI_K4_SPLIT")) ctx->k4Split = atoi(e) != 0;
     if (ctx->cfg.min_inliers == 0) ctx->cfg.min_inliers = 20;
     if (ctx->cfg.test_min_inliers == 0) ctx->cfg.test_min_inliers = 5;
     if (ctx->cfg.fallback_max_iters == 0) ctx->cfg.fallback_max_iters = 1000;
@@ -477,7 +490,7 @@ pgi_status pgi_destroy(pgi_ctx *ctx)
     cudaFree(ctx->d_pairId); cudaFree(ctx->d_hypOffset); cudaFree(ctx->d_bits); cudaFree(ctx->d_hyp);
     cudaFree(ctx->d_state); cudaFree(ctx->d_masks); cudaFree(ctx->d_fbCounts); cudaFree(ctx->d_maskOffset);
     cudaFree(ctx->d_verdicts); cudaFree(ctx->d_fbSols); cudaFree(ctx->d_fbSolsF); cudaFree(ctx->d_counters);
-    cudaFree(ctx->d_k3Scratch);
+    cudaFree(ctx->d_k3Scratch); cudaFree(ctx->d_dkList); cudaFree(ctx->d_dkCtl);
     cudaFree(ctx->d_stFocal); cudaFree(ctx->d_stSize); cudaFree(ctx->d_stKpOff); cudaFree(ctx->d_stKp); cudaFree(ctx->d_stPv); cudaFree(ctx->d_stM);
     cudaFreeHost(ctx->h_pairId); cudaFreeHost(ctx->h_hypOffset); cudaFreeHost(ctx->h_hyp);
     cudaFreeHost(ctx->h_maskOffset); cudaFreeHost(ctx->h_verdicts); cudaFreeHost(ctx->h_counters);

@@ -89,6 +89,8 @@ struct WaveArgs {
     uint8_t *fbCounts;  // n x kFbChunk
     unsigned long long *counters;  // [0] corr evals, [1] fallback pairs, [2] fallback models
     uint32_t *k3Scratch;  // n x 8: votes[4], arrival ticket of the K3 point-range CTAs (all zero between launches)
+    uint32_t *dkList;     // n x kFbChunk: (pair, iteration) slots of the chunk whose degree-10 polynomial awaits its roots
+    uint32_t *dkCtl;      // [0] entries in dkList, [1] next entry to hand out (zeroed before every chunk)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -381,6 +383,138 @@ __global__ void __launch_bounds__(128, 4) k4_fallback_solve(WaveArgs a, int chun
     float4 *outF = a.fbSolsF + ((size_t)w * kFbChunk + j) * 30;
     for (int q = 0; q < n; q++) {
         const double *e = out + q * 9;
+        outF[q * 3 + 0] = make_float4((float)e[0], (float)e[1], (float)e[2], (float)e[3]);
+        outF[q * 3 + 1] = make_float4((float)e[4], (float)e[5], (float)e[6], (float)e[7]);
+        outF[q * 3 + 2] = make_float4((float)e[8], 0.f, 0.f, 0.f);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// K4 as three kernels (the default): the Durand-Kerner root solve is ~45 % of a minimal solve and its sweep count
+// differs from polynomial to polynomial, so with one thread per solve a warp runs as long as its slowest lane
+// (17 of 32 lanes active in the sweeps of k4_fallback_solve).  Here
+//   K4a  one thread per (pair, iteration): sample -> null space -> elimination -> polynomial; parks EE (36), b (39),
+//        c (11) and the degree in the slot's 90-double solution record and appends the slot to a work list;
+//   K4b  persistent lanes: every lane pulls the next polynomial from the list the moment its current one has
+//        converged (register-resident roots, the same dkSweep sequence per polynomial) -> roots into the slot's
+//        FP32-record area (20 doubles);
+//   K4c  one thread per (pair, iteration): roots -> essential matrices, overwriting the parked data with the
+//        solutions + their FP32 copies, exactly what k4_fallback_solve leaves behind.
+// Per polynomial the arithmetic is the same sequence of operations as fivePoint(): bit-identical solutions.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool k4SlotActive(const WaveArgs &a, int chunk, uint32_t g, uint32_t &w, uint32_t &j)
+{
+    w = g / kFbChunk;
+    j = g % kFbChunk;
+    if (w >= a.n) return false;
+    const SlotState &s = a.state[w];
+    if (!(s.flags & ST_FB_ACTIVE)) return false;
+    return chunk * kFbChunk + (int)j < s.maxIters;
+}
+
+__global__ void __launch_bounds__(128, 4) k4a_polynomial(WaveArgs a, int chunk)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t w, j;
+    if (!k4SlotActive(a, chunk, g, w, j)) return;
+    const SlotState &s = a.state[w];
+    const int it = chunk * kFbChunk + (int)j;
+    const uint32_t pid = a.pairId[w];
+    const double4 *rows = reinterpret_cast<const double4 *>(a.corr) + a.offset[pid];
+    const uint32_t *smp = a.samplerTab + ((size_t)s.tableIdx * a.fbMaxIters + it) * 5;
+    double x1[10], x2[10];
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        const double4 c = rows[smp[i]];
+        x1[2 * i] = c.x; x1[2 * i + 1] = c.y; x2[2 * i] = c.z; x2[2 * i + 1] = c.w;
+    }
+    double Vt[81], A[200], A1[100], inv[100], b[39], R6[60], c[11];
+    const int n = fivePointFront<false>(x1, x2, Vt, A, A1, inv, b, R6, c);
+    const size_t slot = (size_t)w * kFbChunk + j;
+    double *park = a.fbSols + slot * 90;
+    for (int k = 0; k < 36; k++) park[k] = Vt[45 + k];
+    for (int k = 0; k < 39; k++) park[36 + k] = b[k];
+    for (int k = 0; k < 11; k++) park[75 + k] = c[k];
+    park[86] = (double)n;
+    if (n == 10) {
+        a.dkList[atomicAdd(a.dkCtl, 1u)] = (uint32_t)slot;
+    } else {  // vanishing leading coefficients (rare): generic-degree solve in place
+        Cx roots[10];
+        dkSolveGeneric(c, n, roots, kDkMaxSweeps, kDkTolSq);
+        double *r = reinterpret_cast<double *>(a.fbSolsF + slot * 30);
+        for (int k = 0; k < n; k++) { r[2 * k] = roots[k].re; r[2 * k + 1] = roots[k].im; }
+    }
+}
+
+__global__ void __launch_bounds__(128, 4) k4b_roots(WaveArgs a)
+{
+    const uint32_t total = a.dkCtl[0];
+    Cx roots[10];
+    double co[11];
+    uint32_t slot = 0;
+    int sweeps = 0;
+    bool have = false, exhausted = false;
+    for (;;) {
+        if (!have && !exhausted) {
+            const uint32_t e = atomicAdd(a.dkCtl + 1, 1u);
+            if (e < total) {
+                slot = a.dkList[e];
+                const double *c = a.fbSols + (size_t)slot * 90 + 75;
+#pragma unroll
+                for (int i = 0; i <= 10; i++) co[i] = c[i];
+                Cx p{1, 0};
+                const Cx r{1, 1};
+#pragma unroll
+                for (int i = 0; i < 10; i++) {  // cv::solvePoly's start vector (dkSolveFixed)
+                    roots[i] = p;
+                    p = cmul(p, r);
+                }
+                sweeps = 0;
+                have = true;
+            } else
+                exhausted = true;
+        }
+        if (!__any_sync(0xffffffffu, have)) break;
+        if (have) {
+            const double md = dkSweep<10>(co, roots);
+            ++sweeps;
+            if (md <= kDkTolSq || sweeps >= kDkMaxSweeps) {
+                double *r = reinterpret_cast<double *>(a.fbSolsF + (size_t)slot * 30);
+#pragma unroll
+                for (int i = 0; i < 10; i++) {
+                    r[2 * i] = roots[i].re;
+                    r[2 * i + 1] = fabs(roots[i].im) < 1e-100 ? 0.0 : roots[i].im;
+                }
+                have = false;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128, 4) k4c_solutions(WaveArgs a, int chunk)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t w, j;
+    if (!k4SlotActive(a, chunk, g, w, j)) return;
+    const size_t slot = (size_t)w * kFbChunk + j;
+    double *out = a.fbSols + slot * 90;
+    float4 *outF = a.fbSolsF + slot * 30;
+    double EE[36], b[39];
+    Cx roots[10];
+    for (int k = 0; k < 36; k++) EE[k] = out[k];
+    for (int k = 0; k < 39; k++) b[k] = out[36 + k];
+    const int n = (int)out[86];
+    {
+        const double *r = reinterpret_cast<const double *>(outF);
+        for (int k = 0; k < n; k++) roots[k] = Cx{r[2 * k], r[2 * k + 1]};
+    }
+    double E[90];
+    const int cnt = fivePointFinish(EE, b, roots, n, E, 10);
+    a.fbCounts[slot] = (uint8_t)cnt;
+    for (int q = 0; q < cnt; q++) {
+        const double *e = E + q * 9;
+        for (int k = 0; k < 9; k++) out[q * 9 + k] = e[k];
         outF[q * 3 + 0] = make_float4((float)e[0], (float)e[1], (float)e[2], (float)e[3]);
         outF[q * 3 + 1] = make_float4((float)e[4], (float)e[5], (float)e[6], (float)e[7]);
         outF[q * 3 + 2] = make_float4((float)e[8], 0.f, 0.f, 0.f);

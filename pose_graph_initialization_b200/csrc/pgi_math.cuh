@@ -495,23 +495,20 @@ __device__ inline void pmulz(const double *a, int la, const double *b, int lb, d
 // lane solves alone (K2 on small waves): a lone lane's local memory is spread over 32-lane-interleaved lines and
 // thrashes L1, shared memory does not.  Same operations on the same operands either way.
 constexpr int kFivePointWs = 81 + 200 + 100 + 100 + 39 + 60;
-template <bool CYCLE_JUMP, bool EXT_WS = false>
-__device__ inline int fivePoint(const double x1[10], const double x2[10], double *Eout, int maxOut, int dkMaxIters,
-                                double dkTolSq, double *ws = nullptr)
+
+// Front half of the kernel: null space of the 5 epipolar constraints (Vt rows 5..8 = EE), the 10x20 constraint
+// matrix, its elimination, the three 13-coefficient rows b and the degree-10 determinant polynomial c (ascending).
+// Returns the polynomial's degree n (10 unless leading coefficients vanish).
+template <bool EXT_WS>
+__device__ __forceinline__ int fivePointFront(const double x1[10], const double x2[10], double *Vt /*81*/, double *A /*200*/,
+                                              double *A1 /*100*/, double *inv /*100*/, double *b /*39*/, double *R6 /*60*/,
+                                              double c[11])
 {
-    double VtL[EXT_WS ? 1 : 81], AL[EXT_WS ? 1 : 200], A1L[EXT_WS ? 1 : 100], invL[EXT_WS ? 1 : 100], bL[EXT_WS ? 1 : 39],
-        R6L[EXT_WS ? 1 : 60];
-    double *const Vt = EXT_WS ? ws : VtL;
-    double *const A = EXT_WS ? ws + 81 : AL;
-    double *const A1 = EXT_WS ? ws + 281 : A1L;
-    double *const inv = EXT_WS ? ws + 381 : invL;
-    double *const b = EXT_WS ? ws + 481 : bL;
-    double *const R6 = EXT_WS ? ws + 520 : R6L;  // rows 4..9 of inv*A2
     for (int i = 0; i < 81; i++) Vt[i] = 0.0;
     for (int i = 0; i < 5; i++) {
-        const double a = x1[2 * i], b = x1[2 * i + 1], c = x2[2 * i], d = x2[2 * i + 1];
+        const double a = x1[2 * i], bb = x1[2 * i + 1], cc = x2[2 * i], d = x2[2 * i + 1];
         double *q = Vt + 9 * i;
-        q[0] = a * c; q[1] = b * c; q[2] = c; q[3] = a * d; q[4] = b * d; q[5] = d; q[6] = a; q[7] = b; q[8] = 1.0;
+        q[0] = a * cc; q[1] = bb * cc; q[2] = cc; q[3] = a * d; q[4] = bb * d; q[5] = d; q[6] = a; q[7] = bb; q[8] = 1.0;
     }
     double W[5];
     cvJacobiSVD<9, 5, 9, false>(Vt, W, nullptr);
@@ -541,7 +538,6 @@ __device__ inline int fivePoint(const double x1[10], const double x2[10], double
             for (int k = 0; k < 13; k++) b[i * 13 + k] = row1[k] - row2[k];
         }
     }
-    double c[11];
     {
         double det[11], m1[7], m2[7], mn[7], t[11];
         for (int k = 0; k < 11; k++) det[k] = 0.0;
@@ -559,15 +555,16 @@ __device__ inline int fivePoint(const double x1[10], const double x2[10], double
         for (int k = 0; k < 11; k++) det[k] += t[k];
         for (int k = 0; k < 11; k++) c[k] = det[10 - k];
     }
-    Cx roots[10];
     int n = 10;
     for (; n > 1; n--)
         if (fabs(c[n]) + 0.0 > DBL_EPSILON) break;
-    if (n == 10)
-        dkSolveFixed<10, CYCLE_JUMP>(c, roots, dkMaxIters, dkTolSq);
-    else
-        dkSolveGeneric(c, n, roots, dkMaxIters, dkTolSq);
+    return n;
+}
 
+// Back half: every real root z gives (x, y) from the 3x3 system b(z) and the essential matrix x E0 + y E1 + z E2 + E3.
+__device__ __forceinline__ int fivePointFinish(const double *EE /*4 x 9*/, const double *b /*39*/, const Cx *roots, int n,
+                                               double *Eout, int maxOut)
+{
     int count = 0;
     for (int i = 0; i < n; i++) {
         if (fabs(roots[i].im) > 1e-10) continue;
@@ -595,6 +592,28 @@ __device__ inline int fivePoint(const double x1[10], const double x2[10], double
         if (count >= maxOut && maxOut < 10) break;
     }
     return count;
+}
+
+template <bool CYCLE_JUMP, bool EXT_WS = false>
+__device__ inline int fivePoint(const double x1[10], const double x2[10], double *Eout, int maxOut, int dkMaxIters,
+                                double dkTolSq, double *ws = nullptr)
+{
+    double VtL[EXT_WS ? 1 : 81], AL[EXT_WS ? 1 : 200], A1L[EXT_WS ? 1 : 100], invL[EXT_WS ? 1 : 100], bL[EXT_WS ? 1 : 39],
+        R6L[EXT_WS ? 1 : 60];
+    double *const Vt = EXT_WS ? ws : VtL;
+    double *const A = EXT_WS ? ws + 81 : AL;
+    double *const A1 = EXT_WS ? ws + 281 : A1L;
+    double *const inv = EXT_WS ? ws + 381 : invL;
+    double *const b = EXT_WS ? ws + 481 : bL;
+    double *const R6 = EXT_WS ? ws + 520 : R6L;  // rows 4..9 of inv*A2
+    double c[11];
+    const int n = fivePointFront<EXT_WS>(x1, x2, Vt, A, A1, inv, b, R6, c);
+    Cx roots[10];
+    if (n == 10)
+        dkSolveFixed<10, CYCLE_JUMP>(c, roots, dkMaxIters, dkTolSq);
+    else
+        dkSolveGeneric(c, n, roots, dkMaxIters, dkTolSq);
+    return fivePointFinish(Vt + 45, b, roots, n, Eout, maxOut);
 }
 
 // ---------------------------------------------------------------------------------------------
