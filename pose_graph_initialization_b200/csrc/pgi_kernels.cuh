@@ -449,11 +449,16 @@ __global__ void __launch_bounds__(128, 4) k4a_polynomial(WaveArgs a, int chunk)
 
 __global__ void __launch_bounds__(128, 4) k4b_roots(WaveArgs a)
 {
+    // ~2 % of the polynomials never reach the tolerance: their sweeps fall into a short floating-point cycle and would
+    // hold a lane (and the end of the kernel) for all kDkMaxSweeps sweeps.  Brent's cycle detection on the bitwise root
+    // state (snapshot in shared memory, one column per lane) jumps to the state sweep kDkMaxSweeps would produce:
+    // identical to running every sweep (dkSolveFixed<., true>, checked against the plain loop in the parity tests).
+    __shared__ double sSnap[20][128];
     const uint32_t total = a.dkCtl[0];
     Cx roots[10];
     double co[11];
     uint32_t slot = 0;
-    int sweeps = 0;
+    int sweeps = 0, power = 1, lam = 0, drain = -1;  // drain >= 0: sweeps left after a detected cycle, no more checks
     bool have = false, exhausted = false;
     for (;;) {
         if (!have && !exhausted) {
@@ -469,17 +474,47 @@ __global__ void __launch_bounds__(128, 4) k4b_roots(WaveArgs a)
                 for (int i = 0; i < 10; i++) {  // cv::solvePoly's start vector (dkSolveFixed)
                     roots[i] = p;
                     p = cmul(p, r);
+                    sSnap[2 * i][threadIdx.x] = roots[i].re;
+                    sSnap[2 * i + 1][threadIdx.x] = roots[i].im;
                 }
-                sweeps = 0;
+                sweeps = 0; power = 1; lam = 0; drain = -1;
                 have = true;
             } else
                 exhausted = true;
         }
         if (!__any_sync(0xffffffffu, have)) break;
         if (have) {
-            const double md = dkSweep<10>(co, roots);
-            ++sweeps;
-            if (md <= kDkTolSq || sweeps >= kDkMaxSweeps) {
+            bool finished = false;
+            if (drain == 0) {
+                finished = true;
+            } else {
+                const double md = dkSweep<10>(co, roots);
+                ++sweeps; ++lam;
+                if (drain > 0) {
+                    finished = --drain == 0;
+                } else if (md <= kDkTolSq || sweeps >= kDkMaxSweeps) {
+                    finished = true;
+                } else {
+                    bool same = true;
+#pragma unroll
+                    for (int i = 0; i < 10; i++)
+                        same &= (__double_as_longlong(roots[i].re) == __double_as_longlong(sSnap[2 * i][threadIdx.x])) &&
+                                (__double_as_longlong(roots[i].im) == __double_as_longlong(sSnap[2 * i + 1][threadIdx.x]));
+                    if (same) {  // period lam: state(kDkMaxSweeps) == state(sweeps + (kDkMaxSweeps - sweeps) % lam)
+                        drain = (kDkMaxSweeps - sweeps) % lam;
+                        finished = drain == 0;
+                    } else if (power == lam) {
+#pragma unroll
+                        for (int i = 0; i < 10; i++) {
+                            sSnap[2 * i][threadIdx.x] = roots[i].re;
+                            sSnap[2 * i + 1][threadIdx.x] = roots[i].im;
+                        }
+                        power *= 2;
+                        lam = 0;
+                    }
+                }
+            }
+            if (finished) {
                 double *r = reinterpret_cast<double *>(a.fbSolsF + (size_t)slot * 30);
 #pragma unroll
                 for (int i = 0; i < 10; i++) {

@@ -76,3 +76,26 @@ def test_status_codes(engine):
     assert len(empty) == 0
     st = engine.stats()
     assert st["launches"] > 0 and st["h2d_bytes"] > 0
+
+
+def test_three_kernel_k4_is_bit_identical_to_the_one_kernel_k4(monkeypatch):
+    """PGI_K4_SPLIT selects K4a/K4b/K4c (lane-refill Durand-Kerner) or the one-kernel solve at pgi_create: the two
+    must leave the same verdict bytes (same per-polynomial sweep sequence, same solutions in the same order)."""
+    from pose_graph_initialization_b200 import Engine
+
+    rng = np.random.default_rng(41)
+    sizes = [5, 9, 64, 500, 1200, 2000, 2000, 777]
+    pairs = [two_view(n, 0.35, rng)[0] for n in sizes]
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    outs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("PGI_K4_SPLIT", flag)
+        e = Engine(device=0)
+        try:
+            e.register_pairs(np.vstack(pairs), off, [THR] * len(sizes))
+            v, m = e.run_wave(np.arange(len(sizes)), None, None, flags=WAVE_FALLBACK, want_masks=True)
+            outs.append((v.tobytes(), m.tobytes(), int(v["accepted"].sum())))
+        finally:
+            e.close()
+    assert outs[0][:2] == outs[1][:2]
+    assert outs[0][2] >= 5  # the comparison is about real fallback runs
