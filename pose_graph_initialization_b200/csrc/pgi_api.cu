@@ -60,6 +60,7 @@ struct pgi_ctx {
     uint2 *d_stPv = nullptr, *d_stM = nullptr;
     size_t capStFocal = 0, capStSize = 0, capStKpOff = 0, capStKp = 0, capStPv = 0, capStM = 0;
     uint32_t *d_dkList = nullptr, *d_dkCtl = nullptr;  // work list of the split K4 (K4a -> K4b -> K4c)
+    uint32_t k4aSmem = 0;  // PGI_K4A_SMEM: dynamic shared memory per K4a CTA, an occupancy throttle (L2 footprint of the 5 KB stacks)
     uint32_t k4bCtas = 2;  // K4b CTAs per SM (PGI_K4B_CTAS): fewer lanes = more polynomials per lane = better refill balance
     bool k4Split = true;   // PGI_K4_SPLIT=0 selects the one-kernel k4_fallback_solve
     uint32_t *d_k3Scratch = nullptr;  // per wave slot: K3 vote totals + arrival ticket (zero between launches)
@@ -359,12 +360,14 @@ pgi_status submitWave(pgi_ctx *ctx, const Registration &r, uint32_t n, const uin
                                   (size_t)((smemPts + 31) / 32) * 4;  // + inlier bit mask of the LO refit
             if (k5Smem > 40 * 1024)  // static shared memory (~4 KB) counts towards the 48 KB default limit
                 CK(cudaFuncSetAttribute(k5_fallback_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k5Smem));
+            if (ctx->k4aSmem > 40 * 1024)
+                CK(cudaFuncSetAttribute(k4a_polynomial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->k4aSmem));
             ctx->nChunks = std::min(chunks, kMaxChunks);
             for (int c = 0; c < ctx->nChunks; c++) {
                 const uint32_t threads = n * kFbChunk;
                 if (ctx->k4Split) {
                     CK(cudaMemsetAsync(ctx->d_dkCtl, 0, 8, s));
-                    k4a_polynomial<<<(threads + 127) / 128, 128, 0, s>>>(a, c);
+                    k4a_polynomial<<<(threads + 127) / 128, 128, ctx->k4aSmem, s>>>(a, c);
                     k4b_roots<<<std::min<uint32_t>((threads + 127) / 128, 148u * ctx->k4bCtas), 128, 0, s>>>(a);
                     k4c_solutions<<<(threads + 127) / 128, 128, 0, s>>>(a, c);
                     ctx->stats.launches += 2;
@@ -450,6 +453,7 @@ pgi_status pgi_create(const pgi_config *cfg, pgi_ctx **out)
     pgi_ctx *ctx = new pgi_ctx();
     ctx->cfg = *cfg;
     if (const char *e = getenv("PGI_K4_SPLIT")) ctx->k4Split = atoi(e) != 0;
+    if (const char *e = getenv("PGI_K4A_SMEM")) ctx->k4aSmem = (uint32_t)std::max(0, std::min(200 * 1024, atoi(e)));
     if (const char *e = getenv("PGI_K4B_CTAS")) ctx->k4bCtas = (uint32_t)std::max(1, std::min(4, atoi(e)));
     if (ctx->cfg.min_inliers == 0) ctx->cfg.min_inliers = 20;
     if (ctx->cfg.test_min_inliers == 0) ctx->cfg.test_min_inliers = 5;

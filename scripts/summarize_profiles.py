@@ -80,6 +80,8 @@ def summarize_launches(path, tag):
 
 if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    if len(sys.argv) > 2:  # summarise on the GPU box into a directory that travels back (gpurun_out/ is capped at 64 MiB)
+        OUT = os.path.abspath(sys.argv[2])
     os.makedirs(OUT, exist_ok=True)
     for p in sorted(glob.glob(os.path.join(SRC, "prof_*.ncu-rep"))):
         summarize_rep(p, tag)
