@@ -413,7 +413,10 @@ __device__ __forceinline__ bool k4SlotActive(const WaveArgs &a, int chunk, uint3
     return chunk * kFbChunk + (int)j < s.maxIters;
 }
 
-__global__ void __launch_bounds__(128, 4) k4a_polynomial(WaveArgs a, int chunk)
+#ifndef PGI_K4A_MINB
+#define PGI_K4A_MINB 4
+#endif
+__global__ void __launch_bounds__(128, PGI_K4A_MINB) k4a_polynomial(WaveArgs a, int chunk)
 {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t w, j;
