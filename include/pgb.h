@@ -120,6 +120,23 @@ uint32_t pgb_commit_wave(pgb_builder *b, const pgi_verdict *verdicts, uint32_t n
  * pgb_wave_status tells the driver what the open wave waits for. */
 int32_t pgb_set_partition(pgb_builder *b, int32_t rank, int32_t world);
 int32_t pgb_wave_status(pgb_builder *b);
+
+/* Native driver of one wave (single rank): pgb_next_wave, then engine rounds (submit / wait / pgb_commit_wave) until
+ * the wave is committed — the loop of PoseGraphBuilder::processImages' worker (pose_graph_builder.h:352-715) with the
+ * engine behind two function pointers whose signatures are those of pgi_submit_wave / pgi_wait_wave (pgi.h), so the
+ * product passes exactly those two and its pgi_ctx.  Host state is guarded by an internal mutex that is released while
+ * the engine works; pgb_set_fallback_verdicts_some takes the same mutex and may be called from another thread.
+ * Returns PGB_WAVE_DONE, PGB_WAVE_NEED_EXCHANGE (several ranks: the caller exchanges records and calls again), or the
+ * engine's negative status.  `stats` (optional) accumulates rounds and seconds. */
+typedef int32_t (*pgb_submit_fn)(void *engine, uint32_t n, const uint32_t *pair_id, const uint32_t *hyp_offset,
+                                 const double *hyp_q_t, uint32_t flags);
+typedef int32_t (*pgb_wait_fn)(void *engine, pgi_verdict *out, uint8_t *masks_or_null);
+typedef struct pgb_drive_stats {
+    double engine_s, host_s;
+    uint32_t rounds, items;
+} pgb_drive_stats;
+int32_t pgb_run_wave(pgb_builder *b, uint32_t wave_size, pgb_submit_fn submit, pgb_wait_fn wait, void *engine,
+                     uint32_t flags, pgb_drive_stats *stats);
 uint32_t pgb_wave_size(pgb_builder *b);
 void pgb_export_records(pgb_builder *b, pgb_record *out);
 uint32_t pgb_import_records(pgb_builder *b, const pgb_record *in);

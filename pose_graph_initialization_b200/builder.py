@@ -55,7 +55,7 @@ RECORD_DTYPE = np.dtype([("valid", np.uint8), ("has_hyp", np.uint8), ("has_path_
 WAVE_DONE, WAVE_NEED_GPU, WAVE_NEED_EXCHANGE = 0, 1, 2
 
 PGB_EXPORTS = ["pgb_create", "pgb_destroy", "pgb_remaining", "pgb_set_fallback_verdicts", "pgb_set_fallback_verdicts_some",
-               "pgb_queue_size", "pgb_queue_pairs", "pgb_set_partition", "pgb_wave_status", "pgb_wave_size",
+               "pgb_queue_size", "pgb_queue_pairs", "pgb_set_partition", "pgb_wave_status", "pgb_wave_size", "pgb_run_wave",
                "pgb_export_records", "pgb_import_records", "pgb_next_wave",
                "pgb_commit_wave", "pgb_edge_count", "pgb_copy_edges", "pgb_log_count", "pgb_copy_log", "pgb_get_counters",
                "pgb_astar"]
@@ -75,6 +75,7 @@ def _host_lib():
         lib.pgb_commit_wave.restype = C.c_uint32
         lib.pgb_import_records.restype = C.c_uint32
         lib.pgb_wave_size.restype = C.c_uint32
+        lib.pgb_run_wave.restype = C.c_int32
         lib.pgb_wave_status.restype = C.c_int32
         lib.pgb_set_partition.restype = C.c_int32
         for name in PGB_EXPORTS[1:]:
@@ -85,6 +86,10 @@ def _host_lib():
 
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class DriveStats(C.Structure):
+    _fields_ = [("engine_s", C.c_double), ("host_s", C.c_double), ("rounds", C.c_uint32), ("items", C.c_uint32)]
 
 
 class HostBuilder:
@@ -143,6 +148,14 @@ class HostBuilder:
         items = np.zeros(max_items, dtype=ITEM_DTYPE)
         n = self.lib.pgb_next_wave(self.h, C.c_uint32(max_items), _ptr(items))
         return items[:n]
+
+    def run_wave(self, wave_size, submit_fn, wait_fn, engine_handle, flags, stats=None):
+        """pgb_run_wave: the native driver of one wave.  submit_fn / wait_fn are C function pointers with the signatures
+        of pgi_submit_wave / pgi_wait_wave (the product passes exactly those two and the engine's pgi_ctx)."""
+        st = stats if stats is not None else DriveStats()
+        rc = int(self.lib.pgb_run_wave(self.h, C.c_uint32(wave_size), submit_fn, wait_fn, engine_handle, C.c_uint32(flags),
+                                       C.byref(st)))
+        return rc
 
     def commit_wave(self, verdicts):
         verdicts = np.ascontiguousarray(verdicts, dtype=VERDICT_DTYPE)
@@ -308,7 +321,7 @@ class PoseGraphBuilder:
                  kImagePath_="", kWorkspacePath_="", kSimilarityGraphPath_="", kFocalLengthPath_="",
                  kUsePathFinding_=True, kUseGPU_=True, kUseEpipolarHashing_=False, *, scene=None, device=0,
                  wave_size=None, prefetch_fallback=True, fallback_wave=1024, overlap_fallback=True, research_window=0,
-                 prefetch_streams=2,
+                 prefetch_streams=2, native_loop=True,
                  group=None, rank=0, world_size=1):
         if not kUseGPU_:
             raise ValueError("the B200 path has no CPU implementation (kUseGPU_ must be true)")
@@ -339,6 +352,9 @@ class PoseGraphBuilder:
         self.engine_fb = None
         self.engine_fb2 = None
         self._exchanger = None
+        # one rank: the wave loop itself runs in C++ (pgb_run_wave calling pgi_submit_wave / pgi_wait_wave directly);
+        # several ranks: the Python loop below, because the record exchange goes through torch.distributed
+        self.native_loop = bool(native_loop)
         self.prefetch_streams = int(prefetch_streams)
         self.timing = {}
 
@@ -478,7 +494,31 @@ class PoseGraphBuilder:
         if self.world > 1:
             import torch
             dev = torch.device("cuda", self.device) if torch.cuda.is_available() else None
-        while True:
+        if self.world == 1 and self.native_loop:
+            lib = _engine.load_library()
+            submit_fn = C.cast(lib.pgi_submit_wave, C.c_void_p)
+            wait_fn = C.cast(lib.pgi_wait_wave, C.c_void_p)
+            st = DriveStats()
+            while True:
+                remaining = host.remaining()
+                if remaining == 0:
+                    break
+                if worker is not None:
+                    need = min(Q, (Q - remaining) + self.wave_size)
+                    t_w = time.perf_counter()
+                    with progress:
+                        while state["done_pos"] < need:
+                            progress.wait()
+                    prof["wait_prefetch_s"] += time.perf_counter() - t_w
+                    if state["error"] is not None:
+                        raise state["error"]
+                rc = host.run_wave(self.wave_size, submit_fn, wait_fn, self.engine.h, flags, st)
+                if rc < 0:
+                    raise _engine.PgiError(f"status {rc}: {lib.pgi_last_error(self.engine.h).decode()}")
+                if rc != WAVE_DONE:
+                    raise RuntimeError(f"pgb_run_wave returned {rc}")
+            prof["engine_s"], prof["host_s"], prof["engine_rounds"] = st.engine_s, st.host_s, int(st.rounds)
+        while self.world > 1 or not self.native_loop:
             with progress:
                 remaining = host.remaining()
                 if remaining == 0:

@@ -504,6 +504,11 @@ struct Pool {
 }  // namespace
 
 struct pgb_builder {
+    std::mutex driveMu;  // guards the host state between pgb_run_wave and pgb_set_fallback_verdicts_some (other thread)
+    std::vector<pgb_item> driveItems;
+    std::vector<uint32_t> driveIds, driveHoff;
+    std::vector<double> driveHyp;
+    std::vector<pgi_verdict> driveVerdicts;
     pgb_config cfg;
     Pool pool;
     uint32_t V = 0;
@@ -831,6 +836,7 @@ int32_t pgb_set_fallback_verdicts(pgb_builder *b, const pgi_verdict *verdicts, u
 int32_t pgb_set_fallback_verdicts_some(pgb_builder *b, const uint32_t *pair_ids, const pgi_verdict *verdicts, uint64_t n)
 {
     if (!b || !verdicts || !pair_ids) return -1;
+    std::lock_guard<std::mutex> lk(b->driveMu);
     for (uint64_t i = 0; i < n; i++) {
         if (pair_ids[i] >= b->P) return -1;
         b->fbCache[pair_ids[i]] = verdicts[i];
@@ -940,6 +946,54 @@ int32_t pgb_set_partition(pgb_builder *b, int32_t rank, int32_t world)
 }
 
 int32_t pgb_wave_status(pgb_builder *b) { return (b && b->waveOpen) ? b->status : PGB_WAVE_DONE; }
+
+int32_t pgb_run_wave(pgb_builder *b, uint32_t wave_size, pgb_submit_fn submit, pgb_wait_fn wait, void *engine, uint32_t flags,
+                     pgb_drive_stats *stats)
+{
+    if (!b || !submit || !wait || wave_size == 0) return -1;
+    double t0 = nowSec();
+    uint32_t n;
+    int32_t status;
+    {
+        std::lock_guard<std::mutex> lk(b->driveMu);
+        b->driveItems.resize(wave_size);
+        n = pgb_next_wave(b, wave_size, b->driveItems.data());
+        status = pgb_wave_status(b);
+    }
+    double t1 = nowSec();
+    if (stats) stats->host_s += t1 - t0;
+    while (status == PGB_WAVE_NEED_GPU) {
+        // the (pair, hypothesis) tuples of this round, in wave order
+        b->driveIds.clear();
+        b->driveHyp.clear();
+        b->driveHoff.assign(1, 0u);
+        for (uint32_t i = 0; i < n; i++) {
+            const pgb_item &it = b->driveItems[i];
+            if (!it.need_gpu) continue;
+            b->driveIds.push_back(it.pair_id);
+            if (it.has_hyp) b->driveHyp.insert(b->driveHyp.end(), it.hyp, it.hyp + 7);
+            b->driveHoff.push_back((uint32_t)(b->driveHyp.size() / 7));
+        }
+        const uint32_t m = (uint32_t)b->driveIds.size();
+        b->driveVerdicts.resize(std::max<uint32_t>(m, 1));
+        int32_t rc = submit(engine, m, b->driveIds.data(), b->driveHoff.data(), b->driveHyp.empty() ? nullptr : b->driveHyp.data(), flags);
+        if (rc < 0) return rc;
+        rc = wait(engine, b->driveVerdicts.data(), nullptr);
+        if (rc < 0) return rc;
+        for (uint32_t i = 0; i < m; i++) b->driveVerdicts[i].pair_id = b->driveIds[i];
+        t0 = nowSec();
+        if (stats) { stats->engine_s += t0 - t1; stats->rounds += 1; stats->items += m; }
+        {
+            std::lock_guard<std::mutex> lk(b->driveMu);
+            pgb_commit_wave(b, b->driveVerdicts.data(), m);
+            status = pgb_wave_status(b);
+            if (status != PGB_WAVE_DONE) n = pgb_next_wave(b, wave_size, b->driveItems.data());
+        }
+        t1 = nowSec();
+        if (stats) stats->host_s += t1 - t0;
+    }
+    return status;
+}
 uint32_t pgb_wave_size(pgb_builder *b) { return b ? (uint32_t)b->wave.size() : 0; }
 
 // One record per wave position; a rank fills the positions it owns and leaves the others zero, so a byte-wise SUM

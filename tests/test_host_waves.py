@@ -109,3 +109,45 @@ def test_similarity_threshold_filters_queue(oracle, small_scene):
     host = B.HostBuilder(small_scene, host_threads=1, lazy_fallback=True, **cfg)
     drive(host, eng, 8, True)
     compare_logs(host.log(), olog)
+
+
+@pytest.mark.parametrize("wave,lazy", [(7, True), (64, False), (1000, False)])
+def test_native_wave_driver_matches_sequential_oracle(oracle, small_scene, oracle_run, wave, lazy):
+    """pgb_run_wave (the C++ loop: next_wave -> engine rounds -> commit) with the engine behind the two function pointers
+    it takes in production (pgi_submit_wave / pgi_wait_wave); here they are ctypes callbacks over the oracle stand-in."""
+    import ctypes as C
+
+    olog, ostats = oracle_run
+    eng = OracleEngine(oracle, small_scene)
+    host = B.HostBuilder(small_scene, host_threads=4, lazy_fallback=lazy, **CFG)
+    if not lazy:
+        fb = np.zeros(host.n_pairs, dtype=B.VERDICT_DTYPE)
+        for p in range(host.n_pairs):
+            fb[p] = eng.verdict(p, None, path=False, fallback=True)
+        host.set_fallback_verdicts(fb)
+    pending = {}
+
+    @C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_double), C.c_uint32)
+    def submit(_ctx, n, pair_id, hyp_offset, hyp, _flags):
+        out = np.zeros(n, dtype=B.VERDICT_DTYPE)
+        for i in range(n):
+            h = None
+            if hyp_offset[i + 1] > hyp_offset[i]:
+                h = np.array([hyp[7 * hyp_offset[i] + k] for k in range(7)])
+            out[i] = eng.verdict(int(pair_id[i]), h, path=True, fallback=lazy)
+        pending["v"] = out
+        return 0
+
+    @C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p)
+    def wait(_ctx, out, _masks):
+        v = pending.pop("v")
+        C.memmove(out, v.ctypes.data, v.nbytes)
+        return 0
+
+    st = B.DriveStats()
+    while host.remaining() > 0:
+        assert host.run_wave(wave, submit, wait, None, 1, st) == B.WAVE_DONE
+    assert st.rounds > 0 and st.items > 0
+    compare_logs(host.log(), olog)
+    assert len(host.edges()) == ostats["edges"]
+    assert host.counters()["path_accepted"] == ostats["path_accepted"]
