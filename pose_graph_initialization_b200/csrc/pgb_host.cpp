@@ -222,6 +222,22 @@ struct Overlay {
         edgePos.clear();
         lookup.clear();
     }
+    // drop every entry added by positions >= pos (entries are appended in position order everywhere)
+    void truncate(uint32_t pos)
+    {
+        size_t keep = edges.size();
+        while (keep > 0 && edgePos[keep - 1] >= pos) --keep;
+        for (size_t ei = keep; ei < edges.size(); ei++) {
+            const Edge &e = edges[ei];
+            lookup.erase(edgeKey(e.src, e.dst));
+            for (uint32_t v : {e.src, e.dst}) {
+                std::vector<OvAdj> &l = byVertex[v];
+                while (!l.empty() && l.back().pos >= pos) l.pop_back();
+            }
+        }
+        edges.resize(keep);
+        edgePos.resize(keep);
+    }
     void add(const Edge &e, uint32_t pos)
     {
         const uint32_t ei = (uint32_t)edges.size();
@@ -523,6 +539,7 @@ struct pgb_builder {
     std::deque<Item> pending;  // re-queued items, in queue order, ahead of `order[nextInOrder..]`
     Graph graph;
     Visibility vis, visPred;
+    std::vector<Visibility> visCkpt;  // simulated table before positions 32, 64, ... of the open wave (rebuildOverlay)
     Overlay overlay;
     std::vector<Item> wave;
     bool waveOpen = false;
@@ -566,14 +583,29 @@ Edge edgeOf(const Item &it, const Outcome &o)
     return e;
 }
 
-// Rebuild the overlay and the simulated visibility from the current predictions; positions whose hasLink answer
-// changed lose their search result.
-void rebuildOverlay(pgb_builder *b)
+// Rebuild the overlay and the simulated visibility from the current predictions, starting at wave position `from`
+// (the first position whose prediction changed: everything before it is unchanged, and so is the state those
+// positions leave behind); positions whose hasLink answer changed lose their search result.  The simulated table is
+// checkpointed every kCkptStride positions so that a late `from` only replays the tail of the wave.
+constexpr uint32_t kCkptStride = 32;
+void rebuildOverlay(pgb_builder *b, uint32_t from = 0)
 {
     const double t0 = nowSec();
-    b->overlay.clear();
-    b->visPred = b->vis;
-    for (uint32_t k = 0; k < b->wave.size(); k++) {
+    uint32_t start = (from / kCkptStride) * kCkptStride;
+    if (start > 0 && start / kCkptStride - 1 >= b->visCkpt.size()) start = 0;  // no checkpoint that far (first build)
+    if (start == 0) {
+        b->overlay.clear();
+        b->visPred = b->vis;
+    } else {
+        b->overlay.truncate(start);
+        b->visPred = b->visCkpt[start / kCkptStride - 1];
+    }
+    for (uint32_t k = start; k < b->wave.size(); k++) {
+        if (k > start && k % kCkptStride == 0) {
+            const size_t ci = k / kCkptStride - 1;
+            if (b->visCkpt.size() <= ci) b->visCkpt.resize(ci + 1);
+            b->visCkpt[ci] = b->visPred;
+        }
         Item &it = b->wave[k];
         const bool vis = b->visPred.hasLink(it.src, it.dst);  // pose_graph_builder.h:456-457 at position k
         if (it.searched && vis != it.visible) it.searched = false;
@@ -753,7 +785,7 @@ uint32_t advanceWave(pgb_builder *b)
             for (uint32_t v : it.expanded)
                 if (b->minChangedPos[v] < m) { it.searched = false; break; }
         }
-        rebuildOverlay(b);
+        rebuildOverlay(b, firstChanged);
     }
     const double t0 = nowSec();
     for (Item &it : b->wave) commitPosition(b, it);

@@ -151,3 +151,50 @@ def test_native_wave_driver_matches_sequential_oracle(oracle, small_scene, oracl
     compare_logs(host.log(), olog)
     assert len(host.edges()) == ostats["edges"]
     assert host.counters()["path_accepted"] == ostats["path_accepted"]
+
+
+def _synthetic_verdict(sc, pair_id, path_ok, inliers):
+    from helpers import quat_from_rot
+
+    v = np.zeros(1, dtype=B.VERDICT_DTYPE)[0]
+    s, d = sc["pair_views"][pair_id]
+    R, t = S.relative_gt(sc, int(s), int(d))
+    v["pair_id"], v["accepted"], v["branch"] = pair_id, 1, 1 if path_ok else 2
+    v["inlier_count"], v["n_corr"] = inliers, 50
+    v["q"], v["t"] = quat_from_rot(R), t / np.linalg.norm(t)
+    v["status"], v["test_passed"] = (0 if path_ok else 1), path_ok
+    return v
+
+
+@pytest.mark.parametrize("threads", [1, 8])
+def test_committed_graph_is_independent_of_the_wave_size_at_scale(threads):
+    """4,950 pairs with synthetic verdicts that are pure functions of (pair, hypothesis bits): the committed log and
+    edges must be byte-identical for every wave size (wave 1 IS the sequential semantics).  Exercises the overlay
+    truncation and the visibility checkpoints of rebuildOverlay on waves far longer than the oracle-backed tests."""
+    sc = S.make_scene(n_views=100, n_corr=50, outlier_ratio=0.3, seed=2, n_points=500)
+    P = len(sc["pair_views"])
+    fb = np.zeros(P, dtype=B.VERDICT_DTYPE)
+    for p in range(P):
+        fb[p] = _synthetic_verdict(sc, p, False, 30 + p % 15)
+    outs = {}
+    for wave in (1, 37, 256, 2048):
+        host = B.HostBuilder(sc, similarity_threshold=0.0, host_threads=threads, lazy_fallback=False)
+        host.set_fallback_verdicts(fb)
+        while host.remaining() > 0:
+            items = host.next_wave(wave)
+            while host.wave_status() != B.WAVE_DONE:
+                todo = items[items["need_gpu"] > 0]
+                v = np.zeros(len(todo), dtype=B.VERDICT_DTYPE)
+                for i, it in enumerate(todo):
+                    ok = bool((int(it["pair_id"]) + int(abs(it["hyp"][4]) * 1e6)) % 3 == 0) if it["has_hyp"] else False
+                    p = int(it["pair_id"])
+                    v[i] = _synthetic_verdict(sc, p, ok, 20 + int(abs(it["hyp"][5]) * 1e6) % 25 if ok else 30 + p % 15)
+                host.commit_wave(v)
+                if host.wave_status() != B.WAVE_DONE:
+                    items = host.next_wave(wave)
+        lg = host.log()
+        outs[wave] = (lg[[n for n in lg.dtype.names if n != "touchedNodes"]].tobytes(), host.edges().tobytes(),
+                      host.counters()["path_accepted"])
+    assert outs[1][2] > 500  # plenty of path-accepted edges, i.e. plenty of prediction changes inside the waves
+    for wave in (37, 256, 2048):
+        assert outs[wave][:2] == outs[1][:2], wave
