@@ -85,6 +85,10 @@ typedef struct pgb_counters {
     uint64_t waves, items_speculated, items_requeued, astar_runs, astar_reruns, verdict_cache_hits;
     uint64_t astar_pops, astar_pushes; /* heap traffic of all searches (touched nodes / pushed nodes) */
     double sec_astar, sec_commit, sec_visibility;
+    uint64_t gpu_searches;      /* searches answered by the device backend (K6)                          */
+    uint64_t gpu_search_redo;   /* device searches repeated on the host (slab overflow)                  */
+    uint64_t search_mismatches; /* PGB_SEARCH_CHECK=1: device results that differ from the host search   */
+    double sec_search_gpu;      /* wall time inside the device backend                                   */
 } pgb_counters;
 
 /* sim: V x V row-major similarity matrix (the text file of imagesimilarity_graph.h:108-171 already parsed).
@@ -137,6 +141,23 @@ typedef struct pgb_drive_stats {
 } pgb_drive_stats;
 int32_t pgb_run_wave(pgb_builder *b, uint32_t wave_size, pgb_submit_fn submit, pgb_wait_fn wait, void *engine,
                      uint32_t flags, pgb_drive_stats *stats);
+
+/* Device search backend: with it, the speculative A* searches of a wave round (graph_traversal.h:679-870) run as ONE
+ * batched device call instead of on the host thread pool — the two function pointers have the signatures of
+ * pgi_graph_apply / pgi_graph_search (pgi.h) and the product passes exactly those and its pgi_ctx, after
+ * pgi_graph_init with the table of pgb_copy_sim_table.  The host mirrors its graph to the device (committed edges at
+ * every commit, the open wave's predicted edges before a round), composes the poses of the returned vertex paths
+ * itself (recoverPath, graph_traversal.h:290-348) and repeats on the host any search the device reports as unfinished.
+ * Rounds with fewer than min_batch searches stay on the host pool.  Results are identical either way
+ * (tests/test_gpu_astar.py; PGB_SEARCH_CHECK=1 re-checks every device search at run time). */
+typedef int32_t (*pgb_graph_apply_fn)(void *engine, uint32_t n_entries, const pgi_adj_entry *entries,
+                                      const uint32_t *committed_count, const uint32_t *total_count);
+typedef int32_t (*pgb_graph_search_fn)(void *engine, uint32_t n, const pgi_query *queries, uint32_t max_depth,
+                                       double weight, pgi_search_result *results, uint32_t *expanded_bits);
+int32_t pgb_set_search_backend(pgb_builder *b, pgb_graph_apply_fn apply, pgb_graph_search_fn search, void *engine,
+                               uint32_t min_batch);
+/* The V x V table the A* heuristic reads: clamp(similarity(next, to), 0, 1) at [to * V + next] (graph_traversal.h:594). */
+void pgb_copy_sim_table(pgb_builder *b, double *out);
 uint32_t pgb_wave_size(pgb_builder *b);
 void pgb_export_records(pgb_builder *b, pgb_record *out);
 uint32_t pgb_import_records(pgb_builder *b, const pgb_record *in);

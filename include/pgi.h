@@ -150,6 +150,59 @@ int32_t pgi_estimate_pose(pgi_ctx *ctx, const double *corr_xy4, uint64_t n, doub
 int32_t pgi_test_pose(pgi_ctx *ctx, const double *corr_xy4, uint64_t n, double thr, uint64_t min_inliers,
                       const double *pose_q_t, uint64_t *inlier_number_out);
 
+/* ---- A* path search on the device (K6) ---------------------------------------------------------------------
+ * AStarTraversal<ImageSimilarityHeuristics>::getPath, graph_traversal.h:679-870, with the arguments of
+ * pose_graph_builder.h:834-841 (returnMultiple = true, one path tested), batched: one warp per (src, dst) query,
+ * std::priority_queue's push_heap / pop_heap order replayed exactly, so a query returns the path
+ * the reference's search returns.  The host (pgb.h) keeps the pose graph; this is its device mirror:
+ * per-vertex edge lists in insertion order (pose_graph.h:219-220), committed entries first, then the entries
+ * PREDICTED by the positions of the open speculative wave, tagged with position + 1.  A query with cutoff k sees the
+ * committed entries and the predicted ones of positions < k.  The composed pose (recoverPath, graph_traversal.h:
+ * 290-348) is left to the caller, who owns the edge poses: the result carries the vertex path. */
+typedef struct pgi_adj_entry {
+    uint32_t vertex, index; /* edge list of `vertex`, slot `index`                                  */
+    uint32_t next;          /* the other endpoint (graph_traversal.h:838-840)                       */
+    uint32_t tag;           /* 0: committed, p + 1: predicted by wave position p                    */
+    double score;           /* PoseGraphEdge score = inlierNumber / matches.size()  (PGB:645-654)   */
+} pgi_adj_entry;
+
+typedef struct pgi_query {
+    uint32_t src, dst; /* search from src to dst                                                    */
+    uint32_t cutoff;   /* predicted entries with tag <= cutoff are part of the graph                */
+    uint32_t reserved;
+} pgi_query;
+
+typedef struct pgi_search_result {
+    uint32_t touched;  /* nodes popped: touchedNodes_ (graph_traversal.h:750)                       */
+    uint32_t pushes;   /* nodes pushed                                                              */
+    uint16_t path[8];  /* vertices src .. dst of the tested path (path_len entries)                 */
+    uint8_t found;     /* destination popped (graph_traversal.h:766)                                */
+    uint8_t path_len;
+    uint8_t status;    /* 0 ok; 1 heap slab full, 2 arena full, 3 vertex without edge list: the caller repeats
+                          the search with its own (host) implementation                             */
+    uint8_t pad;
+    uint32_t reserved;
+} pgi_search_result;
+
+typedef struct pgi_search_stats {
+    double ms_search;      /* K6 kernel time (CUDA events)                                          */
+    uint64_t launches;     /* K6 + apply kernels launched                                           */
+    uint64_t queries, pops, pushes, overflows;
+    uint64_t h2d_bytes, d2h_bytes;
+} pgi_search_stats;
+
+/* (Re)create the device graph for n_views vertices (<= 65535).  sim_to_next is the V x V similarity table already
+ * clamped to [0,1] and TRANSPOSED: sim_to_next[to * V + next] = clamp(similarity(next, to))  (graph_traversal.h:594). */
+pgi_status pgi_graph_init(pgi_ctx *ctx, uint32_t n_views, const double *sim_to_next);
+/* Write edge-list entries and set the per-vertex counts (both arrays have n_views entries; total >= committed). */
+pgi_status pgi_graph_apply(pgi_ctx *ctx, uint32_t n_entries, const pgi_adj_entry *entries,
+                           const uint32_t *committed_count, const uint32_t *total_count);
+/* Run n searches.  expanded_bits receives n x ceil(V/32) words: bit v set iff vertex v's edge list was read
+ * (graph_traversal.h:814-817).  Synchronous. max_depth <= 7. */
+pgi_status pgi_graph_search(pgi_ctx *ctx, uint32_t n, const pgi_query *queries, uint32_t max_depth, double weight,
+                            pgi_search_result *results, uint32_t *expanded_bits);
+pgi_status pgi_graph_stats(pgi_ctx *ctx, pgi_search_stats *out, int32_t reset);
+
 pgi_status pgi_get_stats(pgi_ctx *ctx, pgi_stats *out);
 pgi_status pgi_reset_stats(pgi_ctx *ctx);
 

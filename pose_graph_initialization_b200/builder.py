@@ -6,7 +6,7 @@ File-system inputs of the reference (image path, workspace HDF5 caches, similari
 list_with_focals.txt) are replaced by an in-memory scene dict (scene.py); every other
 constructor argument keeps its name, meaning and default (examples/cpp_example.cpp:32-66).
 
-Multi-GPU: one process per GPU.  Pairs are owned by contiguous id ranges; each rank verifies
+Multi-GPU: one process per GPU.  Pair p is owned by rank p % world (interleaved); each rank verifies
 the wave items it owns and the 160-byte verdict records are all-gathered (torch.distributed: NCCL over
 NVLink on device buffers, gloo on CPU tensors in the tests) so that every rank runs the same deterministic
 commit.  With world_size == 1 no collective is issued.
@@ -44,7 +44,9 @@ class PgbCounters(C.Structure):
     _fields_ = [(k, C.c_uint64) for k in ("pairs_popped", "committed", "path_accepted", "fallback_accepted", "rejected",
                                           "skipped", "waves", "items_speculated", "items_requeued", "astar_runs",
                                           "astar_reruns", "verdict_cache_hits", "astar_pops", "astar_pushes")] + \
-               [(k, C.c_double) for k in ("sec_astar", "sec_commit", "sec_visibility")]
+               [(k, C.c_double) for k in ("sec_astar", "sec_commit", "sec_visibility")] + \
+               [(k, C.c_uint64) for k in ("gpu_searches", "gpu_search_redo", "search_mismatches")] + \
+               [("sec_search_gpu", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -56,7 +58,7 @@ WAVE_DONE, WAVE_NEED_GPU, WAVE_NEED_EXCHANGE = 0, 1, 2
 
 PGB_EXPORTS = ["pgb_create", "pgb_destroy", "pgb_remaining", "pgb_set_fallback_verdicts", "pgb_set_fallback_verdicts_some",
                "pgb_queue_size", "pgb_queue_pairs", "pgb_set_partition", "pgb_wave_status", "pgb_wave_size", "pgb_run_wave",
-               "pgb_export_records", "pgb_import_records", "pgb_next_wave",
+               "pgb_export_records", "pgb_import_records", "pgb_next_wave", "pgb_set_search_backend", "pgb_copy_sim_table",
                "pgb_commit_wave", "pgb_edge_count", "pgb_copy_edges", "pgb_log_count", "pgb_copy_log", "pgb_get_counters",
                "pgb_astar"]
 
@@ -78,6 +80,7 @@ def _host_lib():
         lib.pgb_run_wave.restype = C.c_int32
         lib.pgb_wave_status.restype = C.c_int32
         lib.pgb_set_partition.restype = C.c_int32
+        lib.pgb_set_search_backend.restype = C.c_int32
         for name in PGB_EXPORTS[1:]:
             getattr(lib, name).argtypes = None
         lib._pgb_ready = True
@@ -110,6 +113,7 @@ class HostBuilder:
             raise RuntimeError(f"pgb_create failed: {st}")
         self.h = h
         self.n_pairs = len(pv)
+        self._sim_shape = range(len(sim))
         self._items = None
 
     def close(self):
@@ -196,6 +200,27 @@ class HostBuilder:
         c = PgbCounters()
         self.lib.pgb_get_counters(self.h, C.byref(c))
         return c.as_dict()
+
+    def sim_table(self):
+        """The V x V table the A* heuristic reads (transposed, clamped) — what pgi_graph_init takes."""
+        V = len(self._sim_shape)
+        out = np.zeros((V, V), dtype=np.float64)
+        self.lib.pgb_copy_sim_table(self.h, _ptr(out))
+        return out
+
+    def set_search_backend(self, engine, min_batch=8):
+        """Run the speculative A* searches on the engine's device (K6): pgi_graph_init + pgb_set_search_backend with
+        the engine's own pgi_graph_apply / pgi_graph_search entry points.  engine=None restores the host pool."""
+        lib = _engine.load_library()
+        if engine is None:
+            if self.lib.pgb_set_search_backend(self.h, None, None, None, C.c_uint32(0)) != 0:
+                raise RuntimeError("pgb_set_search_backend failed")
+            return
+        engine.graph_init(self.sim_table())
+        apply_fn = C.cast(lib.pgi_graph_apply, C.c_void_p)
+        search_fn = C.cast(lib.pgi_graph_search, C.c_void_p)
+        if self.lib.pgb_set_search_backend(self.h, apply_fn, search_fn, engine.h, C.c_uint32(min_batch)) != 0:
+            raise RuntimeError("pgb_set_search_backend failed")
 
     def astar(self, src, dst):
         hyp = np.zeros(7)
@@ -321,7 +346,7 @@ class PoseGraphBuilder:
                  kImagePath_="", kWorkspacePath_="", kSimilarityGraphPath_="", kFocalLengthPath_="",
                  kUsePathFinding_=True, kUseGPU_=True, kUseEpipolarHashing_=False, *, scene=None, device=0,
                  wave_size=None, prefetch_fallback=True, fallback_wave=1024, overlap_fallback=True, research_window=0,
-                 prefetch_streams=2, native_loop=True,
+                 prefetch_streams=2, native_loop=True, gpu_search=True, gpu_search_min_batch=16,
                  group=None, rank=0, world_size=1):
         if not kUseGPU_:
             raise ValueError("the B200 path has no CPU implementation (kUseGPU_ must be true)")
@@ -329,6 +354,10 @@ class PoseGraphBuilder:
             raise NotImplementedError("epipolar hashing (matcher.h) is outside the hot path (SURVEY §8f row 3)")
         if scene is None:
             raise ValueError("scene=... is required (the reference's HDF5/1DSfM inputs are replaced by scene.py)")
+        if world_size > 1 and not prefetch_fallback:
+            # the exchange records carry path verdicts only: a non-owner rank could never learn a remote pair's
+            # fallback verdict and the ranks' wave loops would diverge
+            raise ValueError("world_size > 1 requires prefetch_fallback=True")
         self.scene = scene
         self.cfg = dict(similarity_threshold=kSimilarityThreshold_, minimum_inlier_number=kMinimumInlierNumber_,
                         minimum_point_number=kMinimumPointNumber_, maximum_search_depth=kMaximumSearchDepth_,
@@ -355,6 +384,9 @@ class PoseGraphBuilder:
         # one rank: the wave loop itself runs in C++ (pgb_run_wave calling pgi_submit_wave / pgi_wait_wave directly);
         # several ranks: the Python loop below, because the record exchange goes through torch.distributed
         self.native_loop = bool(native_loop)
+        # speculative A* searches of a wave round as one batched device call (K6) instead of the host thread pool
+        self.gpu_search = bool(gpu_search)
+        self.gpu_search_min_batch = int(gpu_search_min_batch)
         self.prefetch_streams = int(prefetch_streams)
         self.timing = {}
 
@@ -431,6 +463,8 @@ class PoseGraphBuilder:
         t_reg = time.perf_counter()
         host = HostBuilder(self.scene, lazy_fallback=not self.prefetch_fallback, **self.cfg)
         self.host = host
+        if self.gpu_search:
+            host.set_search_backend(self.engine, self.gpu_search_min_batch)
         lock = threading.Lock()
         progress = threading.Condition(lock)
         state = {"done_pos": 0, "error": None}
@@ -576,4 +610,5 @@ class PoseGraphBuilder:
         edges = host.edges()
         self.log = host.log()
         self.counters = host.counters()
+        self.search_stats = self.engine.search_stats() if self.gpu_search else {}
         return PoseGraph(len(self.scene["focal"]), edges)

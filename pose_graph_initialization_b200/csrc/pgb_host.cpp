@@ -26,6 +26,8 @@
 #include <chrono>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <condition_variable>
 #include <deque>
@@ -120,15 +122,19 @@ struct Graph {
 // is kept as is.
 struct Visibility {
     uint32_t V = 0, words = 0;
+    uint64_t nLinks = 0;  // set bits of `link`; V(V-1)/2 = every pair linked: the table can never change again
     std::vector<uint64_t> link, nb;
-    std::vector<uint32_t> fifo;
     void init(uint32_t v)
     {
         V = v;
         words = (v + 63) / 64;
+        nLinks = 0;
         link.assign((size_t)V * words, 0);
         nb.assign((size_t)V * words, 0);
     }
+    // Every pair is linked: hasLink is true for all a != b, and addLink can only touch the neighbour sets, which are
+    // read by nothing but the creation of new links (visibility_table.h:80-83, :113-114).
+    bool complete() const { return nLinks == (uint64_t)V * (V - 1) / 2; }
     bool get(const std::vector<uint64_t> &m, uint32_t r, uint32_t c) const { return (m[(size_t)r * words + (c >> 6)] >> (c & 63)) & 1; }
     void set(std::vector<uint64_t> &m, uint32_t r, uint32_t c) { m[(size_t)r * words + (c >> 6)] |= 1ull << (c & 63); }
     bool hasLink(uint32_t a, uint32_t b) const
@@ -136,17 +142,12 @@ struct Visibility {
         if (a == b) return false;
         return get(link, std::min(a, b), std::max(a, b));
     }
-    void pushRow(uint32_t r)
-    {
-        const uint64_t *row = &nb[(size_t)r * words];
-        for (uint32_t w = 0; w < words; w++) {
-            uint64_t x = row[w];
-            while (x) {
-                fifo.push_back(w * 64 + (uint32_t)__builtin_ctzll(x));
-                x &= x - 1;
-            }
-        }
-    }
+    // The reference walks a FIFO of neighbour ids (visibility_table.h:76-118).  What the walk leaves behind does not
+    // depend on the order or on repeated visits: a vertex is expanded (its neighbour set queued) the first time it is
+    // met without a link to `from`, its neighbour set only gains {from, to} during the walk (both are skipped when
+    // met), and every later visit of the same vertex changes nothing.  So the reachable set is computed with bit
+    // rows (pending |= nb[v] & ~visited) instead of queueing up to V ids per expansion.
+    std::vector<uint64_t> pending, visited;
     bool addLink(uint32_t from_, uint32_t to_)
     {
         if (from_ == to_) return false;
@@ -155,19 +156,30 @@ struct Visibility {
         set(nb, to, from);
         if (get(link, from, to)) return false;
         set(link, from, to);
-        fifo.clear();
-        pushRow(from);
-        pushRow(to);
-        for (size_t head = 0; head < fifo.size(); ++head) {
-            const uint32_t v = fifo[head];
-            if (v == from || v == to) continue;
-            const uint32_t first = std::min(v, from), second = std::max(v, from);
-            if (!get(link, first, second)) {
-                set(link, first, second);
-                pushRow(v);
+        ++nLinks;
+        pending.assign(words, 0);
+        visited.assign(words, 0);
+        const uint64_t *rf = &nb[(size_t)from * words], *rt = &nb[(size_t)to * words];
+        for (uint32_t w = 0; w < words; w++) pending[w] = rf[w] | rt[w];
+        for (;;) {
+            uint32_t w = 0;
+            while (w < words && pending[w] == 0) ++w;
+            if (w == words) break;
+            while (pending[w]) {
+                const uint32_t v = w * 64 + (uint32_t)__builtin_ctzll(pending[w]);
+                pending[w] &= pending[w] - 1;
+                visited[v >> 6] |= 1ull << (v & 63);
+                if (v == from || v == to) continue;
+                const uint32_t first = std::min(v, from), second = std::max(v, from);
+                if (!get(link, first, second)) {  // `!hasPair1 || !hasPair1` (:108)
+                    set(link, first, second);
+                    ++nLinks;
+                    const uint64_t *rv = &nb[(size_t)v * words];
+                    for (uint32_t x = 0; x < words; x++) pending[x] |= rv[x] & ~visited[x];
+                }
+                set(nb, v, from);
+                set(nb, v, to);
             }
-            set(nb, v, from);
-            set(nb, v, to);
         }
         return true;
     }
@@ -238,6 +250,10 @@ struct Overlay {
         edges.resize(keep);
         edgePos.resize(keep);
     }
+    bool hasEither(uint32_t s, uint32_t d) const
+    {
+        return lookup.find(edgeKey(s, d)) != lookup.end() || lookup.find(edgeKey(d, s)) != lookup.end();
+    }
     void add(const Edge &e, uint32_t pos)
     {
         const uint32_t ei = (uint32_t)edges.size();
@@ -265,6 +281,23 @@ struct GraphView {
         return nullptr;
     }
 };
+
+// PoseGraphTraversal::recoverPath (graph_traversal.h:290-348): compose T_dst_src along the vertex path.
+template <typename PathT>
+bool recoverPath(const GraphView &gv, const PathT *path, size_t n, SE3 &pose)
+{
+    pose = se3Identity();  // :304
+    for (size_t i = 1; i < n; ++i) {
+        const uint32_t s = path[i - 1], d = path[i];
+        if (const Edge *e = gv.find(s, d))
+            pose = se3Mul(e->T, pose);  // :344
+        else if (const Edge *e2 = gv.find(d, s))
+            pose = se3Mul(se3Inverse(e2->T), pose);  // :342
+        else
+            return false;
+    }
+    return true;
+}
 
 // AStarTraversal<ImageSimilarityHeuristics>::getPath with the arguments of pose_graph_builder.h:834-841.
 void aStar(const GraphView &gv, const double *sim /*transposed*/, uint32_t V, uint32_t from, uint32_t to, size_t maxDepth,
@@ -326,16 +359,8 @@ void aStar(const GraphView &gv, const double *sim /*transposed*/, uint32_t V, ui
             S.path.push_back(v);
             for (uint32_t k = node.parent; k != UINT32_MAX; k = S.arena[k].parent) S.path.push_back(S.arena[k].vertex);
             std::reverse(S.path.begin(), S.path.end());
-            SE3 pose = se3Identity();  // recoverPath :304
-            bool ok = true;
-            for (size_t i = 1; i < S.path.size(); ++i) {
-                const uint32_t s = S.path[i - 1], d = S.path[i];
-                if (const Edge *e = gv.find(s, d))
-                    pose = se3Mul(e->T, pose);  // :344
-                else if (const Edge *e2 = gv.find(d, s))
-                    pose = se3Mul(se3Inverse(e2->T), pose);  // :342
-                else { ok = false; break; }
-            }
+            SE3 pose;
+            const bool ok = recoverPath(gv, S.path.data(), S.path.size(), pose);
             if (ok) {
                 out.found = true;
                 out.pose = pose;
@@ -419,6 +444,8 @@ struct Item {
     uint32_t src = 0, dst = 0;
     uint32_t nCorr = 0;
     bool staticSkip = false;  // no correspondences / fewer than minimum_point_number (pose_graph_builder.h:550-551)
+    bool dupSkip = false;     // the graph (committed, or predicted by an earlier wave position) already has this pair
+                              // in either direction: the reference skips it before anything else (:438-443)
     bool searched = false;    // search result below is consistent with the current overlay
     bool visible = false;
     bool hasHyp = false;
@@ -554,6 +581,18 @@ struct pgb_builder {
     std::vector<pgb_log> log;
     pgb_counters ctr;
     std::vector<AStarScratch> scratch;
+    // device search backend (pgb_set_search_backend): the engine's pgi_graph_apply / pgi_graph_search
+    pgb_graph_apply_fn gpuApply = nullptr;
+    pgb_graph_search_fn gpuSearch = nullptr;
+    void *gpuEngine = nullptr;
+    uint32_t gpuMinBatch = 0;
+    int32_t searchError = 0;     // first engine status of a failed device search (surfaced by pgb_run_wave)
+    bool gpuCheck = false;       // PGB_SEARCH_CHECK=1: every device search is repeated on the host and compared
+    bool ovDirty = true;         // the overlay changed since it was last mirrored to the device
+    std::vector<pgi_adj_entry> gpuEntries, commitEntries;
+    std::vector<uint32_t> gpuCommitted, gpuTotal, gpuBits, gpuTodo;
+    std::vector<pgi_query> gpuQueries;
+    std::vector<pgi_search_result> gpuResults;
 };
 
 namespace {
@@ -588,9 +627,39 @@ Edge edgeOf(const Item &it, const Outcome &o)
 // positions leave behind); positions whose hasLink answer changed lose their search result.  The simulated table is
 // checkpointed every kCkptStride positions so that a late `from` only replays the tail of the wave.
 constexpr uint32_t kCkptStride = 32;
+// pose_graph_builder.h:438-443 as the sequential run would answer it at this position: the overlay holds exactly the
+// edges predicted by the earlier positions while rebuildOverlay walks the wave in order.
+inline bool isDuplicate(const pgb_builder *b, const Item &it)
+{
+    return b->graph.hasEdge(it.src, it.dst) || b->graph.hasEdge(it.dst, it.src) || b->overlay.hasEither(it.src, it.dst);
+}
 void rebuildOverlay(pgb_builder *b, uint32_t from = 0)
 {
     const double t0 = nowSec();
+    b->ovDirty = true;
+    bool allLinked = true;
+    for (const Item &it : b->wave)
+        if (!it.staticSkip && !b->vis.hasLink(it.src, it.dst)) { allLinked = false; break; }
+    if (allLinked) {
+        // Every pair the wave can commit is already linked in the committed table.  addLink on an existing link only
+        // inserts into the two neighbour sets and returns (visibility_table.h:62-73), so no link can appear during this
+        // wave and hasLink answers what the committed table answers: nothing needs to be simulated.  (The neighbour
+        // sets are updated by the real commit, in order.)
+        b->overlay.truncate(from);
+        if (from == 0) b->overlay.clear();
+        for (uint32_t k = from; k < b->wave.size(); k++) {
+            Item &it = b->wave[k];
+            const bool vis = b->vis.hasLink(it.src, it.dst);
+            const bool dup = isDuplicate(b, it);
+            if (it.searched && (vis != it.visible || dup != it.dupSkip)) it.searched = false;
+            it.visible = vis;
+            it.dupSkip = dup;
+            if (!it.staticSkip && !dup && it.pred.known && it.pred.accepted) b->overlay.add(edgeOf(it, it.pred), k);
+        }
+        b->visCkpt.clear();
+        b->ctr.sec_visibility += nowSec() - t0;
+        return;
+    }
     uint32_t start = (from / kCkptStride) * kCkptStride;
     if (start > 0 && start / kCkptStride - 1 >= b->visCkpt.size()) start = 0;  // no checkpoint that far (first build)
     if (start == 0) {
@@ -608,9 +677,11 @@ void rebuildOverlay(pgb_builder *b, uint32_t from = 0)
         }
         Item &it = b->wave[k];
         const bool vis = b->visPred.hasLink(it.src, it.dst);  // pose_graph_builder.h:456-457 at position k
-        if (it.searched && vis != it.visible) it.searched = false;
+        const bool dup = isDuplicate(b, it);
+        if (it.searched && (vis != it.visible || dup != it.dupSkip)) it.searched = false;
         it.visible = vis;
-        if (!it.staticSkip && it.pred.known && it.pred.accepted) {
+        it.dupSkip = dup;
+        if (!it.staticSkip && !dup && it.pred.known && it.pred.accepted) {
             b->overlay.add(edgeOf(it, it.pred), k);
             b->visPred.addLink(it.src, it.dst);  // :692
         }
@@ -624,7 +695,7 @@ void searchPosition(pgb_builder *b, uint32_t k, AStarScratch &S)
     it.hasHyp = false;
     it.expanded.clear();
     it.touched = it.pushes = 0;
-    if (b->cfg.use_path_finding && it.visible && !it.staticSkip) {  // :569-570
+    if (b->cfg.use_path_finding && it.visible && !it.staticSkip && !it.dupSkip) {  // :569-570
         AStarOut o;
         GraphView gv{&b->graph, &b->overlay, k};
         aStar(gv, b->sim.data(), b->V, it.src, it.dst, (size_t)b->cfg.maximum_search_depth,
@@ -638,14 +709,8 @@ void searchPosition(pgb_builder *b, uint32_t k, AStarScratch &S)
     it.searched = true;
 }
 
-// Search the stale positions below `limit` (pgb_config.reserved can restrict the re-search to a window behind the
-// first stale position; unlimited by default).
-void searchStale(pgb_builder *b, uint32_t limit)
+void searchOnHost(pgb_builder *b, const std::vector<uint32_t> &todo)
 {
-    const double t0 = nowSec();
-    std::vector<uint32_t> todo;
-    for (uint32_t k = 0; k < b->wave.size() && k < limit; k++)
-        if (b->wave[k].mine && !b->wave[k].searched) todo.push_back(k);
     if (b->cfg.host_threads <= 1 || todo.size() < 4) {
         for (uint32_t k : todo) searchPosition(b, k, b->scratch[0]);
     } else {
@@ -658,6 +723,140 @@ void searchStale(pgb_builder *b, uint32_t limit)
             }
         });
     }
+}
+
+// Mirror the open wave's overlay to the device graph: every predicted entry with its slot behind the committed
+// entries of its vertex (tag = wave position + 1), plus the per-vertex counts.
+int32_t uploadOverlay(pgb_builder *b)
+{
+    const uint32_t V = b->V;
+    b->gpuEntries.clear();
+    b->gpuCommitted.resize(V);
+    b->gpuTotal.resize(V);
+    for (uint32_t v = 0; v < V; v++) b->gpuCommitted[v] = b->gpuTotal[v] = (uint32_t)b->graph.byVertex[v].size();
+    for (uint32_t v : b->overlay.touchedVertices) {
+        const std::vector<OvAdj> &l = b->overlay.byVertex[v];
+        const uint32_t base = b->gpuCommitted[v];
+        for (uint32_t j = 0; j < l.size(); j++)
+            b->gpuEntries.push_back(pgi_adj_entry{v, base + j, l[j].a.next, l[j].pos + 1u, l[j].a.score});
+        b->gpuTotal[v] = base + (uint32_t)l.size();
+    }
+    const int32_t rc = b->gpuApply(b->gpuEngine, (uint32_t)b->gpuEntries.size(), b->gpuEntries.data(), b->gpuCommitted.data(),
+                                   b->gpuTotal.data());
+    if (rc == 0) b->ovDirty = false;
+    return rc;
+}
+
+// Search the positions of `todo` with the device backend (K6, pgi_graph_search); positions the device could not
+// finish (slab overflow) and trivially hypothesis-free positions are completed on the host.
+int32_t searchOnDevice(pgb_builder *b, const std::vector<uint32_t> &todo)
+{
+    const double t0 = nowSec();
+    if (b->ovDirty) {
+        const int32_t rc = uploadOverlay(b);
+        if (rc != 0) return rc;
+    }
+    const uint32_t words = (b->V + 31) / 32;
+    b->gpuQueries.clear();
+    b->gpuTodo.clear();
+    for (uint32_t k : todo) {
+        Item &it = b->wave[k];
+        if (b->cfg.use_path_finding && it.visible && !it.staticSkip && !it.dupSkip) {  // pose_graph_builder.h:569-570
+            b->gpuQueries.push_back(pgi_query{it.src, it.dst, k, 0});
+            b->gpuTodo.push_back(k);
+        } else {
+            it.hasHyp = false;
+            it.expanded.clear();
+            it.touched = it.pushes = 0;
+            it.searched = true;
+        }
+    }
+    const uint32_t n = (uint32_t)b->gpuQueries.size();
+    if (n == 0) return 0;
+    b->gpuResults.resize(n);
+    b->gpuBits.resize((size_t)n * words);
+    const int32_t rc = b->gpuSearch(b->gpuEngine, n, b->gpuQueries.data(), (uint32_t)b->cfg.maximum_search_depth,
+                                    b->cfg.traversal_heuristics_weight, b->gpuResults.data(), b->gpuBits.data());
+    if (rc != 0) return rc;
+    std::vector<uint32_t> redo;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t k = b->gpuTodo[i];
+        Item &it = b->wave[k];
+        const pgi_search_result &r = b->gpuResults[i];
+        if (r.status != 0) { redo.push_back(k); continue; }
+        it.touched = r.touched;
+        it.pushes = r.pushes;
+        it.expanded.clear();
+        const uint32_t *bits = b->gpuBits.data() + (size_t)i * words;
+        for (uint32_t w = 0; w < words; w++) {
+            uint32_t x = bits[w];
+            while (x) {
+                it.expanded.push_back(w * 32 + (uint32_t)__builtin_ctz(x));
+                x &= x - 1;
+            }
+        }
+        it.hasHyp = false;
+        if (r.found) {
+            GraphView gv{&b->graph, &b->overlay, k};
+            SE3 pose;
+            if (recoverPath(gv, r.path, r.path_len, pose)) {
+                it.hasHyp = true;
+                it.hyp = pose;
+            } else
+                redo.push_back(k);  // (cannot happen: the path's edges are in the graph the search saw)
+        }
+        it.searched = true;
+    }
+    b->ctr.gpu_searches += n - redo.size();
+    b->ctr.gpu_search_redo += redo.size();
+    b->ctr.sec_search_gpu += nowSec() - t0;
+    if (!redo.empty()) searchOnHost(b, redo);
+    if (b->gpuCheck) {
+        // debug: repeat every device search on the host and compare what the wave logic consumes
+        for (uint32_t i = 0; i < n; i++) {
+            const uint32_t k = b->gpuTodo[i];
+            Item &it = b->wave[k];
+            const bool hasHyp = it.hasHyp;
+            const SE3 hyp = it.hyp;
+            std::vector<uint32_t> exp = it.expanded;
+            const uint32_t touched = it.touched, pushes = it.pushes;
+            searchPosition(b, k, b->scratch[0]);
+            std::vector<uint32_t> expHost = it.expanded;
+            std::sort(exp.begin(), exp.end());
+            std::sort(expHost.begin(), expHost.end());
+            expHost.erase(std::unique(expHost.begin(), expHost.end()), expHost.end());
+            const bool same = hasHyp == it.hasHyp && (!hasHyp || !memcmp(&hyp, &it.hyp, sizeof(SE3))) && touched == it.touched &&
+                              pushes == it.pushes && exp == expHost;
+            if (!same) {
+                if (b->ctr.search_mismatches < 10)
+                    fprintf(stderr, "[pgb] device/host search mismatch at wave position %u (%u -> %u): found %d/%d touched %u/%u pushes %u/%u expanded %zu/%zu\n",
+                            k, it.src, it.dst, (int)hasHyp, (int)it.hasHyp, touched, it.touched, pushes, it.pushes, exp.size(), expHost.size());
+                b->ctr.search_mismatches++;
+            }
+        }
+    }
+    return 0;
+}
+
+// Search the stale positions below `limit` (pgb_config.reserved can restrict the re-search to a window behind the
+// first stale position; unlimited by default).
+void searchStale(pgb_builder *b, uint32_t limit)
+{
+    const double t0 = nowSec();
+    std::vector<uint32_t> todo;
+    for (uint32_t k = 0; k < b->wave.size() && k < limit; k++)
+        if (b->wave[k].mine && !b->wave[k].searched) todo.push_back(k);
+    bool done = false;
+    if (b->gpuSearch && todo.size() >= b->gpuMinBatch && b->V <= 65535u && b->cfg.maximum_search_depth <= 7) {
+        const int32_t rc = searchOnDevice(b, todo);
+        if (rc == 0)
+            done = true;
+        else {
+            b->searchError = rc;
+            fprintf(stderr, "[pgb] device search failed with status %d\n", (int)rc);
+        }
+    }
+    if (!done) searchOnHost(b, todo);
     for (uint32_t k : todo) { b->ctr.astar_pops += b->wave[k].touched; b->ctr.astar_pushes += b->wave[k].pushes; }
     b->ctr.astar_runs += todo.size();
     if (b->rounds > 0) b->ctr.astar_reruns += todo.size();
@@ -672,7 +871,7 @@ uint32_t resolveVerdicts(pgb_builder *b)
         it.needGpu = false;
         if (!it.mine) continue;  // remote positions are resolved by their owner (import)
         it.finalV = it.pathV = nullptr;
-        if (it.staticSkip || !it.searched) continue;  // unsearched positions wait for the window to reach them
+        if (it.staticSkip || it.dupSkip || !it.searched) continue;  // unsearched positions wait for the window to reach them
         if (it.hasHyp) {
             auto pc = b->pathCache.find(makeKey(it.pairId, it.hyp));
             if (pc == b->pathCache.end()) { it.needGpu = true; ++need; continue; }
@@ -724,6 +923,10 @@ void commitPosition(pgb_builder *b, Item &it)
     b->graph.lookup[edgeKey(e.src, e.dst)] = ei;
     b->graph.byVertex[e.src].push_back(Adj{e.dst, ei, e.score});  // pose_graph.h:219-220
     b->graph.byVertex[e.dst].push_back(Adj{e.src, ei, e.score});
+    if (b->gpuApply) {
+        b->commitEntries.push_back(pgi_adj_entry{e.src, (uint32_t)b->graph.byVertex[e.src].size() - 1, e.dst, 0u, e.score});
+        b->commitEntries.push_back(pgi_adj_entry{e.dst, (uint32_t)b->graph.byVertex[e.dst].size() - 1, e.src, 0u, e.score});
+    }
     const double tv = nowSec();
     b->vis.addLink(e.src, e.dst);  // :692
     b->ctr.sec_visibility += nowSec() - tv;
@@ -762,7 +965,7 @@ uint32_t advanceWave(pgb_builder *b)
         bool allKnown = true;
         for (uint32_t k = 0; k < n; k++) {
             Item &it = b->wave[k];
-            if (it.staticSkip) continue;
+            if (it.staticSkip || it.dupSkip) continue;
             if (it.mine ? !it.searched : !it.remoteKnown) { allKnown = false; continue; }
             const Outcome act = outcomeOf(it.finalV);
             if (!act.sameEdge(it.pred)) {
@@ -788,11 +991,20 @@ uint32_t advanceWave(pgb_builder *b)
         rebuildOverlay(b, firstChanged);
     }
     const double t0 = nowSec();
+    b->commitEntries.clear();
     for (Item &it : b->wave) commitPosition(b, it);
     b->wave.clear();
     b->waveOpen = false;
     b->status = PGB_WAVE_DONE;
     b->overlay.clear();
+    if (b->gpuApply) {  // mirror the committed edges of the wave to the device graph
+        b->gpuCommitted.resize(b->V);
+        for (uint32_t v = 0; v < b->V; v++) b->gpuCommitted[v] = (uint32_t)b->graph.byVertex[v].size();
+        const int32_t rc = b->gpuApply(b->gpuEngine, (uint32_t)b->commitEntries.size(), b->commitEntries.data(),
+                                       b->gpuCommitted.data(), b->gpuCommitted.data());
+        if (rc != 0 && b->searchError == 0) b->searchError = rc;
+        b->ovDirty = false;  // device graph == committed graph, no overlay
+    }
     b->ctr.sec_commit += nowSec() - t0;
     return n;
 }
@@ -972,12 +1184,37 @@ uint32_t pgb_commit_wave(pgb_builder *b, const pgi_verdict *verdicts, uint32_t n
 int32_t pgb_set_partition(pgb_builder *b, int32_t rank, int32_t world)
 {
     if (!b || world < 1 || rank < 0 || rank >= world || b->waveOpen) return -1;
+    if (world > 1 && b->cfg.lazy_fallback) return -1;  // records carry path verdicts only: fallback verdicts must be prefetched
     b->rank = rank;
     b->world = world;
     return 0;
 }
 
 int32_t pgb_wave_status(pgb_builder *b) { return (b && b->waveOpen) ? b->status : PGB_WAVE_DONE; }
+
+int32_t pgb_set_search_backend(pgb_builder *b, pgb_graph_apply_fn apply, pgb_graph_search_fn search, void *engine,
+                               uint32_t min_batch)
+{
+    if (!b || b->waveOpen || ((apply == nullptr) != (search == nullptr))) return -1;
+    b->gpuApply = apply;
+    b->gpuSearch = search;
+    b->gpuEngine = engine;
+    b->gpuMinBatch = min_batch;
+    b->ovDirty = true;
+    if (const char *e = getenv("PGB_SEARCH_CHECK")) b->gpuCheck = atoi(e) != 0;
+    if (!apply) return 0;
+    // bring the device graph up to the committed graph (normally empty at this point)
+    std::vector<pgi_adj_entry> entries;
+    b->gpuCommitted.resize(b->V);
+    for (uint32_t v = 0; v < b->V; v++) {
+        const std::vector<Adj> &l = b->graph.byVertex[v];
+        b->gpuCommitted[v] = (uint32_t)l.size();
+        for (uint32_t j = 0; j < l.size(); j++) entries.push_back(pgi_adj_entry{v, j, l[j].next, 0u, l[j].score});
+    }
+    return apply(engine, (uint32_t)entries.size(), entries.data(), b->gpuCommitted.data(), b->gpuCommitted.data());
+}
+
+void pgb_copy_sim_table(pgb_builder *b, double *out) { memcpy(out, b->sim.data(), b->sim.size() * sizeof(double)); }
 
 int32_t pgb_run_wave(pgb_builder *b, uint32_t wave_size, pgb_submit_fn submit, pgb_wait_fn wait, void *engine, uint32_t flags,
                      pgb_drive_stats *stats)
@@ -991,6 +1228,7 @@ int32_t pgb_run_wave(pgb_builder *b, uint32_t wave_size, pgb_submit_fn submit, p
         b->driveItems.resize(wave_size);
         n = pgb_next_wave(b, wave_size, b->driveItems.data());
         status = pgb_wave_status(b);
+        if (b->searchError) return b->searchError;
     }
     double t1 = nowSec();
     if (stats) stats->host_s += t1 - t0;
@@ -1018,6 +1256,7 @@ int32_t pgb_run_wave(pgb_builder *b, uint32_t wave_size, pgb_submit_fn submit, p
         {
             std::lock_guard<std::mutex> lk(b->driveMu);
             pgb_commit_wave(b, b->driveVerdicts.data(), m);
+            if (b->searchError) return b->searchError;
             status = pgb_wave_status(b);
             if (status != PGB_WAVE_DONE) n = pgb_next_wave(b, wave_size, b->driveItems.data());
         }
@@ -1036,7 +1275,7 @@ void pgb_export_records(pgb_builder *b, pgb_record *out)
     memset(out, 0, (size_t)n * sizeof(pgb_record));
     for (uint32_t k = 0; k < n; k++) {
         const Item &it = b->wave[k];
-        if (!it.mine || it.staticSkip) continue;
+        if (!it.mine || it.staticSkip || it.dupSkip) continue;
         pgb_record &r = out[k];
         r.valid = (it.searched && it.finalV) ? 1 : 0;
         r.has_hyp = it.hasHyp;
@@ -1053,7 +1292,7 @@ uint32_t pgb_import_records(pgb_builder *b, const pgb_record *in)
     const uint32_t n = (uint32_t)b->wave.size();
     for (uint32_t k = 0; k < n; k++) {
         Item &it = b->wave[k];
-        if (it.mine || it.staticSkip) continue;
+        if (it.mine || it.staticSkip || it.dupSkip) continue;
         const pgb_record &r = in[k];
         it.remoteKnown = r.valid != 0;
         it.hasHyp = r.has_hyp != 0;

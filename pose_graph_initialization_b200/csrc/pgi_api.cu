@@ -14,6 +14,7 @@
 
 #include "../../include/pgi.h"
 #include "pgi_kernels.cuh"
+#include "pgi_astar.cuh"
 
 using namespace pgi;
 
@@ -85,6 +86,29 @@ struct pgi_ctx {
     cudaEvent_t evChunk[kMaxChunks][2];
     bool fbLaunched = false;
     pgi_stats stats;
+    // ---- K6: device mirror of the pose graph + per-search slabs (pgi_graph_*) ----
+    AdjDev *d_adj = nullptr;
+    uint32_t gV = 0, gCap = 0, gWords = 0;
+    uint32_t *d_gCounts = nullptr;   // [0, V): committed entries per vertex, [V, 2V): committed + predicted
+    double *d_simT = nullptr;
+    HeapItemDev *d_heaps = nullptr;
+    ArenaNodeDev *d_arenas = nullptr;
+    uint32_t heapCap = 0, arenaCap = 0, searchSlots = 0;
+    pgi_query *d_queries = nullptr;
+    pgi_search_result *d_results = nullptr;
+    uint32_t *d_expBits = nullptr, *d_nextQuery = nullptr;
+    uint32_t queryCap = 0;
+    ApplyEntry *d_apply = nullptr;
+    uint32_t applyCap = 0;
+    ApplyEntry *h_apply = nullptr;
+    uint32_t *h_gCounts = nullptr;
+    pgi_query *h_queries = nullptr;
+    pgi_search_result *h_results = nullptr;
+    uint32_t *h_expBits = nullptr;
+    uint32_t hApplyCap = 0, hQueryCap = 0;
+    int popLookahead = 1;
+    cudaEvent_t evS0 = nullptr, evS1 = nullptr;
+    pgi_search_stats sstats;
 };
 
 namespace {
@@ -427,6 +451,8 @@ pgi_status finishWave(pgi_ctx *ctx)
 
 extern "C" {
 
+static void freeGraph(pgi_ctx *ctx);
+
 const char *pgi_version(void) { return "pgi 0.1 (sm_100a)"; }
 
 int32_t pgi_device_count(void)
@@ -461,6 +487,7 @@ pgi_status pgi_create(const pgi_config *cfg, pgi_ctx **out)
     if (ctx->cfg.fallback_max_iters > (uint32_t)kMaxChunks * kFbChunk) ctx->cfg.fallback_max_iters = kMaxChunks * kFbChunk;
     if (ctx->cfg.threshold_multiplier == 0.0) ctx->cfg.threshold_multiplier = 3.0 / 2.0;
     memset(&ctx->stats, 0, sizeof ctx->stats);
+    memset(&ctx->sstats, 0, sizeof ctx->sstats);
     auto fail = [&](pgi_status s) { pgi_destroy(ctx); return s; };
     if (cudaSetDevice(cfg->device) != cudaSuccess) return fail(PGI_ERR_CUDA);
     {
@@ -491,6 +518,9 @@ pgi_status pgi_destroy(pgi_ctx *ctx)
     if (!ctx) return PGI_OK;
     cudaSetDevice(ctx->cfg.device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    freeGraph(ctx);
+    if (ctx->evS0) cudaEventDestroy(ctx->evS0);
+    if (ctx->evS1) cudaEventDestroy(ctx->evS1);
     freeReg(ctx->reg);
     freeReg(ctx->tmp);
     cudaFree(ctx->d_pairId); cudaFree(ctx->d_hypOffset); cudaFree(ctx->d_bits); cudaFree(ctx->d_hyp);
@@ -718,6 +748,170 @@ int32_t pgi_test_pose(pgi_ctx *ctx, const double *corr_xy4, uint64_t n, double t
     if (st != PGI_OK) return st;
     if (inlier_number_out) *inlier_number_out = s.testCount;
     return (s.flags & ST_TEST_PASSED) ? 1 : 0;
+}
+
+// ---- K6: device pose graph + batched A* -------------------------------------------------------------------
+static void freeGraph(pgi_ctx *ctx)
+{
+    cudaFree(ctx->d_adj); cudaFree(ctx->d_gCounts); cudaFree(ctx->d_simT); cudaFree(ctx->d_heaps); cudaFree(ctx->d_arenas);
+    cudaFree(ctx->d_queries); cudaFree(ctx->d_results); cudaFree(ctx->d_expBits); cudaFree(ctx->d_nextQuery); cudaFree(ctx->d_apply);
+    cudaFreeHost(ctx->h_apply); cudaFreeHost(ctx->h_gCounts); cudaFreeHost(ctx->h_queries); cudaFreeHost(ctx->h_results);
+    cudaFreeHost(ctx->h_expBits);
+    ctx->d_adj = nullptr; ctx->d_gCounts = nullptr; ctx->d_simT = nullptr; ctx->d_heaps = nullptr; ctx->d_arenas = nullptr;
+    ctx->d_queries = nullptr; ctx->d_results = nullptr; ctx->d_expBits = nullptr; ctx->d_nextQuery = nullptr; ctx->d_apply = nullptr;
+    ctx->h_apply = nullptr; ctx->h_gCounts = nullptr; ctx->h_queries = nullptr; ctx->h_results = nullptr; ctx->h_expBits = nullptr;
+    ctx->gV = ctx->gCap = ctx->gWords = 0;
+    ctx->queryCap = ctx->applyCap = ctx->hApplyCap = ctx->hQueryCap = 0;
+    ctx->heapCap = ctx->arenaCap = ctx->searchSlots = 0;
+}
+
+pgi_status pgi_graph_init(pgi_ctx *ctx, uint32_t n_views, const double *sim_to_next)
+{
+    if (!ctx) return PGI_ERR_INVALID;
+    if (!sim_to_next || n_views == 0 || n_views > 65535u) { ctx->err = "bad graph size (1..65535 views)"; return PGI_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->cfg.device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const uint32_t V = n_views;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, ctx->cfg.device));
+    uint32_t slotsPerSm = 16, heapCap = 0;
+    if (const char *e = getenv("PGI_ASTAR_SLOTS_PER_SM")) slotsPerSm = (uint32_t)std::max(4, std::min(48, atoi(e)));
+    slotsPerSm = (slotsPerSm / kAstarWarps) * kAstarWarps;
+    if (const char *e = getenv("PGI_ASTAR_HEAP")) heapCap = (uint32_t)std::max(1024, atoi(e));
+    if (const char *e = getenv("PGI_ASTAR_POP")) ctx->popLookahead = atoi(e) != 0;
+    if (!heapCap) {
+        const uint64_t want = (uint64_t)V * V / 2;
+        heapCap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 65536), 1u << 20);
+    }
+    const uint32_t slots = (uint32_t)prop.multiProcessorCount * slotsPerSm;
+    const uint32_t arenaCap = 16384;
+    if (ctx->gV != V || ctx->heapCap != heapCap || ctx->searchSlots != slots) {
+        freeGraph(ctx);
+        ctx->gV = V; ctx->gCap = V; ctx->gWords = (V + 31) / 32;
+        CK(cudaMalloc((void **)&ctx->d_adj, (size_t)V * ctx->gCap * sizeof(AdjDev)));
+        CK(cudaMalloc((void **)&ctx->d_gCounts, (size_t)2 * V * 4));
+        CK(cudaMalloc((void **)&ctx->d_simT, (size_t)V * V * 8));
+        CK(cudaMalloc((void **)&ctx->d_heaps, (size_t)slots * heapCap * sizeof(HeapItemDev)));
+        CK(cudaMalloc((void **)&ctx->d_arenas, (size_t)slots * arenaCap * sizeof(ArenaNodeDev)));
+        CK(cudaMalloc((void **)&ctx->d_nextQuery, 4));
+        CK(cudaMallocHost((void **)&ctx->h_gCounts, (size_t)2 * V * 4));
+        ctx->heapCap = heapCap; ctx->arenaCap = arenaCap; ctx->searchSlots = slots;
+    }
+    CK(cudaMemsetAsync(ctx->d_gCounts, 0, (size_t)2 * V * 4, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_simT, sim_to_next, (size_t)V * V * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->sstats.h2d_bytes += (uint64_t)V * V * 8;
+    if (!ctx->evS0) { CK(cudaEventCreate(&ctx->evS0)); CK(cudaEventCreate(&ctx->evS1)); }
+    return PGI_OK;
+}
+
+pgi_status pgi_graph_apply(pgi_ctx *ctx, uint32_t n_entries, const pgi_adj_entry *entries, const uint32_t *committed_count,
+                           const uint32_t *total_count)
+{
+    if (!ctx) return PGI_ERR_INVALID;
+    if (!ctx->d_adj) { ctx->err = "pgi_graph_init has not been called"; return PGI_ERR_STATE; }
+    if ((n_entries && !entries) || !committed_count || !total_count) { ctx->err = "null argument"; return PGI_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->cfg.device));
+    const uint32_t V = ctx->gV;
+    for (uint32_t v = 0; v < V; v++)
+        if (total_count[v] < committed_count[v] || total_count[v] > ctx->gCap) { ctx->err = "bad edge-list count"; return PGI_ERR_INVALID; }
+    for (uint32_t i = 0; i < n_entries; i++)
+        if (entries[i].vertex >= V || entries[i].next >= V || entries[i].index >= ctx->gCap) { ctx->err = "edge-list entry out of range"; return PGI_ERR_INVALID; }
+    if (n_entries > ctx->hApplyCap) {
+        const uint32_t cap = std::max<uint32_t>(n_entries * 2, 4096);
+        cudaFreeHost(ctx->h_apply); ctx->h_apply = nullptr; ctx->hApplyCap = 0;
+        cudaFree(ctx->d_apply); ctx->d_apply = nullptr; ctx->applyCap = 0;
+        CK(cudaMallocHost((void **)&ctx->h_apply, (size_t)cap * sizeof(ApplyEntry)));
+        CK(cudaMalloc((void **)&ctx->d_apply, (size_t)cap * sizeof(ApplyEntry)));
+        ctx->hApplyCap = ctx->applyCap = cap;
+    }
+    static_assert(sizeof(ApplyEntry) == sizeof(pgi_adj_entry), "apply entry layout");
+    cudaStream_t s = ctx->stream;
+    memcpy(ctx->h_gCounts, committed_count, (size_t)V * 4);
+    memcpy(ctx->h_gCounts + V, total_count, (size_t)V * 4);
+    CK(cudaMemcpyAsync(ctx->d_gCounts, ctx->h_gCounts, (size_t)2 * V * 4, cudaMemcpyHostToDevice, s));
+    if (n_entries) {
+        memcpy(ctx->h_apply, entries, (size_t)n_entries * sizeof(ApplyEntry));
+        CK(cudaMemcpyAsync(ctx->d_apply, ctx->h_apply, (size_t)n_entries * sizeof(ApplyEntry), cudaMemcpyHostToDevice, s));
+        k6_graph_apply<<<(n_entries + 255) / 256, 256, 0, s>>>(ctx->d_adj, ctx->gCap, ctx->d_apply, n_entries);
+        CK(cudaGetLastError());
+        ctx->sstats.launches += 1;
+    }
+    CK(cudaStreamSynchronize(s));  // the pinned staging buffers are reused by the next call
+    ctx->sstats.h2d_bytes += (uint64_t)2 * V * 4 + (uint64_t)n_entries * sizeof(ApplyEntry);
+    return PGI_OK;
+}
+
+pgi_status pgi_graph_search(pgi_ctx *ctx, uint32_t n, const pgi_query *queries, uint32_t max_depth, double weight,
+                            pgi_search_result *results, uint32_t *expanded_bits)
+{
+    if (!ctx) return PGI_ERR_INVALID;
+    if (!ctx->d_adj) { ctx->err = "pgi_graph_init has not been called"; return PGI_ERR_STATE; }
+    if (n == 0) return PGI_OK;
+    if (!queries || !results || !expanded_bits || max_depth > 7) { ctx->err = "bad argument"; return PGI_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->cfg.device));
+    const uint32_t V = ctx->gV, words = ctx->gWords;
+    for (uint32_t i = 0; i < n; i++)
+        if (queries[i].src >= V || queries[i].dst >= V) { ctx->err = "query vertex out of range"; return PGI_ERR_INVALID; }
+    if (n > ctx->queryCap) {
+        const uint32_t cap = std::max<uint32_t>(n, 4096);
+        cudaFree(ctx->d_queries); cudaFree(ctx->d_results); cudaFree(ctx->d_expBits);
+        cudaFreeHost(ctx->h_queries); cudaFreeHost(ctx->h_results); cudaFreeHost(ctx->h_expBits);
+        ctx->d_queries = nullptr; ctx->d_results = nullptr; ctx->d_expBits = nullptr;
+        ctx->h_queries = nullptr; ctx->h_results = nullptr; ctx->h_expBits = nullptr;
+        ctx->queryCap = ctx->hQueryCap = 0;
+        CK(cudaMalloc((void **)&ctx->d_queries, (size_t)cap * sizeof(pgi_query)));
+        CK(cudaMalloc((void **)&ctx->d_results, (size_t)cap * sizeof(pgi_search_result)));
+        CK(cudaMalloc((void **)&ctx->d_expBits, (size_t)cap * words * 4));
+        CK(cudaMallocHost((void **)&ctx->h_queries, (size_t)cap * sizeof(pgi_query)));
+        CK(cudaMallocHost((void **)&ctx->h_results, (size_t)cap * sizeof(pgi_search_result)));
+        CK(cudaMallocHost((void **)&ctx->h_expBits, (size_t)cap * words * 4));
+        ctx->queryCap = ctx->hQueryCap = cap;
+    }
+    cudaStream_t s = ctx->stream;
+    memcpy(ctx->h_queries, queries, (size_t)n * sizeof(pgi_query));
+    CK(cudaMemcpyAsync(ctx->d_queries, ctx->h_queries, (size_t)n * sizeof(pgi_query), cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(ctx->d_nextQuery, 0, 4, s));
+    SearchArgs a;
+    a.adj = ctx->d_adj; a.cap = ctx->gCap; a.ccnt = ctx->d_gCounts; a.cnt = ctx->d_gCounts + V; a.simT = ctx->d_simT;
+    a.V = V; a.words = words; a.n = n; a.queries = ctx->d_queries; a.maxDepth = max_depth;
+    a.weight = weight; a.oneMinusWeight = 1.0 - weight;
+    a.heaps = ctx->d_heaps; a.heapCap = ctx->heapCap; a.arenas = ctx->d_arenas; a.arenaCap = ctx->arenaCap;
+    a.results = ctx->d_results; a.expandedBits = ctx->d_expBits; a.nextQuery = ctx->d_nextQuery;
+    a.popLookahead = ctx->popLookahead;
+    const uint32_t ctas = std::min<uint32_t>((n + kAstarWarps - 1) / kAstarWarps, ctx->searchSlots / kAstarWarps);
+    const size_t smem = (size_t)kAstarWarps * words * 4;
+    CK(cudaEventRecord(ctx->evS0, s));
+    k6_astar_search<<<ctas, kAstarWarps * 32, smem, s>>>(a);
+    CK(cudaEventRecord(ctx->evS1, s));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ctx->h_results, ctx->d_results, (size_t)n * sizeof(pgi_search_result), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ctx->h_expBits, ctx->d_expBits, (size_t)n * words * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    memcpy(results, ctx->h_results, (size_t)n * sizeof(pgi_search_result));
+    memcpy(expanded_bits, ctx->h_expBits, (size_t)n * words * 4);
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->evS0, ctx->evS1));
+    pgi_search_stats &st = ctx->sstats;
+    st.ms_search += ms;
+    st.launches += 1;
+    st.queries += n;
+    for (uint32_t i = 0; i < n; i++) {
+        st.pops += results[i].touched;
+        st.pushes += results[i].pushes;
+        st.overflows += results[i].status != 0;
+    }
+    st.h2d_bytes += (uint64_t)n * sizeof(pgi_query);
+    st.d2h_bytes += (uint64_t)n * (sizeof(pgi_search_result) + (uint64_t)words * 4);
+    return PGI_OK;
+}
+
+pgi_status pgi_graph_stats(pgi_ctx *ctx, pgi_search_stats *out, int32_t reset)
+{
+    if (!ctx) return PGI_ERR_INVALID;
+    if (out) *out = ctx->sstats;
+    if (reset) memset(&ctx->sstats, 0, sizeof ctx->sstats);
+    return PGI_OK;
 }
 
 pgi_status pgi_get_stats(pgi_ctx *ctx, pgi_stats *out)

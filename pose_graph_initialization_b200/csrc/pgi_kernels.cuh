@@ -211,7 +211,9 @@ __global__ void __launch_bounds__(kCtaThreads, 3) k1_score_hypotheses(WaveArgs a
                 if (lane == 0) {
                     cTest += __popc(bt);
                     cInl += __popc(bi);
-                    bits[i >> 5] = bi;
+                    // only words below ceil(N/32) exist for this pair (a row group past N would spill into the next
+                    // bit buffer / slot); lane 0's i is the first row of the 32-row group
+                    if (i < N) bits[i >> 5] = bi;
                 }
             }
         }

@@ -45,7 +45,8 @@ class PgiStats(C.Structure):
 EXPORTS = [
     "pgi_version", "pgi_device_count", "pgi_create", "pgi_destroy", "pgi_last_error", "pgi_register_pairs",
     "pgi_register_scene", "pgi_share_pairs", "pgi_read_pair", "pgi_submit_wave", "pgi_wait_wave", "pgi_wait_wave_device",
-    "pgi_estimate_pose", "pgi_test_pose", "pgi_get_stats", "pgi_reset_stats", "pgi_dbg_sampson",
+    "pgi_estimate_pose", "pgi_test_pose", "pgi_graph_init", "pgi_graph_apply", "pgi_graph_search", "pgi_graph_stats",
+    "pgi_get_stats", "pgi_reset_stats", "pgi_dbg_sampson",
     "pgi_dbg_five_point", "pgi_dbg_pose_from_essential", "pgi_dbg_fp64_peak",
 ]
 
@@ -85,6 +86,23 @@ def _ptr(a):
 
 def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+ADJ_ENTRY_DTYPE = np.dtype([("vertex", np.uint32), ("index", np.uint32), ("next", np.uint32), ("tag", np.uint32),
+                            ("score", np.float64)], align=True)
+QUERY_DTYPE = np.dtype([("src", np.uint32), ("dst", np.uint32), ("cutoff", np.uint32), ("reserved", np.uint32)], align=True)
+SEARCH_RESULT_DTYPE = np.dtype([("touched", np.uint32), ("pushes", np.uint32), ("path", np.uint16, (8,)), ("found", np.uint8),
+                                ("path_len", np.uint8), ("status", np.uint8), ("pad", np.uint8), ("reserved", np.uint32)],
+                               align=True)
+assert ADJ_ENTRY_DTYPE.itemsize == 24 and QUERY_DTYPE.itemsize == 16 and SEARCH_RESULT_DTYPE.itemsize == 32
+
+
+class PgiSearchStats(C.Structure):
+    _fields_ = [("ms_search", C.c_double)] + [(k, C.c_uint64) for k in ("launches", "queries", "pops", "pushes", "overflows",
+                                                                         "h2d_bytes", "d2h_bytes")]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 class PgiError(RuntimeError):
@@ -208,6 +226,34 @@ class Engine:
         if r < 0:
             self._ck(r)
         return bool(r), int(inl.value)
+
+    # ---- A* on the device (K6) ---------------------------------------------------------------------------
+    def graph_init(self, sim_to_next):
+        """sim_to_next: V x V, clamped and transposed (HostBuilder.sim_table())."""
+        t = _f64(sim_to_next)
+        self._graph_V = len(t)
+        self._ck(self.lib.pgi_graph_init(self.h, C.c_uint32(len(t)), _ptr(t)))
+
+    def graph_apply(self, entries, committed_count, total_count):
+        entries = np.ascontiguousarray(entries, dtype=ADJ_ENTRY_DTYPE)
+        cc = np.ascontiguousarray(committed_count, dtype=np.uint32)
+        tc = np.ascontiguousarray(total_count, dtype=np.uint32)
+        self._ck(self.lib.pgi_graph_apply(self.h, C.c_uint32(len(entries)), _ptr(entries), _ptr(cc), _ptr(tc)))
+
+    def graph_search(self, queries, max_depth=5, weight=0.8):
+        queries = np.ascontiguousarray(queries, dtype=QUERY_DTYPE)
+        n = len(queries)
+        words = (self._graph_V + 31) // 32
+        res = np.zeros(n, dtype=SEARCH_RESULT_DTYPE)
+        bits = np.zeros((n, words), dtype=np.uint32)
+        self._ck(self.lib.pgi_graph_search(self.h, C.c_uint32(n), _ptr(queries), C.c_uint32(max_depth), C.c_double(weight),
+                                           _ptr(res), _ptr(bits)))
+        return res, bits
+
+    def search_stats(self, reset=False):
+        s = PgiSearchStats()
+        self._ck(self.lib.pgi_graph_stats(self.h, C.byref(s), C.c_int32(1 if reset else 0)))
+        return s.as_dict()
 
     # ---- stats / debug -------------------------------------------------------------------------------------
     def stats(self):

@@ -198,3 +198,31 @@ def test_committed_graph_is_independent_of_the_wave_size_at_scale(threads):
     assert outs[1][2] > 500  # plenty of path-accepted edges, i.e. plenty of prediction changes inside the waves
     for wave in (37, 256, 2048):
         assert outs[wave][:2] == outs[1][:2], wave
+
+
+def test_both_directions_of_a_pair_queued_in_one_wave():
+    """Asymmetric similarities queue (i,j) and (j,i) (imagesimilarity_graph.h:149-157); the second one is skipped by the
+    duplicate-edge check (pose_graph_builder.h:438-443) when the first was committed.  The speculative overlay must
+    model that skip: the wave result may not depend on the wave size (wave = 1 is the sequential run)."""
+    from fake_verdicts import dense_scene, drive
+
+    sc = dense_scene(40, n_corr=400, seed=3)
+    rng = np.random.default_rng(8)
+    sim = sc["sim"].copy()
+    iu = np.triu_indices(40, 1)
+    pick = rng.random(len(iu[0])) < 0.5
+    sim[iu[1][pick], iu[0][pick]] = np.round(np.clip(sim[iu[0][pick], iu[1][pick]] - 0.013, 0, 0.999), 3)  # lower triangle differs
+    sc["sim"] = sim
+    rev = np.stack([iu[1][pick], iu[0][pick]], axis=1).astype(np.uint32)
+    sc["pair_views"] = np.concatenate([sc["pair_views"], rev])
+    sc["m_offset"] = np.arange(len(sc["pair_views"]) + 1, dtype=np.uint64) * np.uint64(400)
+    logs = []
+    for wave in (1, 37, 256):
+        host = B.HostBuilder(sc, host_threads=3, lazy_fallback=False, **CFG)
+        drive(host, wave, 400)
+        logs.append((host.log().copy(), host.edges().copy(), host.counters()))
+        host.close()
+    assert logs[0][2]["skipped"] > 0  # the reversed duplicates were met and skipped
+    for lg, ed, _ in logs[1:]:
+        assert lg.tobytes() == logs[0][0].tobytes()
+        assert ed.tobytes() == logs[0][1].tobytes()
