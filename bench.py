@@ -424,7 +424,7 @@ def main():
                                                     "k3_decompose_vote": st_fb["ms_decompose"]},
             "host_s_per_step": {k: timing.get(k) for k in ("prefetch_s", "waves_s", "total_s", "engine_s", "exchange_s", "host_s",
                                                             "wait_prefetch_s", "engine_rounds", "exchanges")},
-            "host_counters": counters, "edges": int(n_edges), "wall_s_resident": wall,
+            "search_stats": getattr(pgb, "search_stats", None), "host_counters": counters, "edges": int(n_edges), "wall_s_resident": wall,
             "cpu_baseline": {"value": cpu["pairs_per_s"], "unit": "pairs/s", "cores": cpu["cores"], "kind": "port",
                              "sample": "%d evenly spaced pairs of the same scene through the oracle's estimatePose "
                                        "(fallback + E->(R,t) vote), %.1f s" % (cpu["pairs"], cpu["seconds"]),

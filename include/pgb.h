@@ -68,6 +68,8 @@ typedef struct pgb_log {  /* one record per pair popped from the queue, in proce
     uint8_t visible, had_path, test_passed, branch, committed, pad[3];
     uint32_t test_count, inlier_number, n_corr, touched_nodes;
     double E[9], q[4], t[3], score;
+    double hyp[7];        /* the hypothesis A* composed for the pair (qx qy qz qw tx ty tz), zero if had_path == 0:
+                             with pair_index it is the (pair, hypothesis) tuple the engine verified */
 } pgb_log;
 
 /* Exchange record of one wave position (multi-rank): filled by the position's owner, zero elsewhere, merged by a
@@ -76,6 +78,7 @@ typedef struct pgb_record {
     uint8_t valid, has_hyp, has_path_verdict, final_is_path;
     uint32_t touched;
     pgi_verdict v;   /* the owner's verdict for (pair, hypothesis) if has_path_verdict */
+    double hyp[7];   /* the hypothesis the owner's search composed (has_hyp): every rank logs the same tuples */
 } pgb_record;
 
 enum { PGB_WAVE_DONE = 0, PGB_WAVE_NEED_GPU = 1, PGB_WAVE_NEED_EXCHANGE = 2 };

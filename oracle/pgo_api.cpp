@@ -185,6 +185,66 @@ int pgo_estimate_pose_batch(const double *corr, const uint64_t *offset, uint64_t
     return used;
 }
 
+// The per-pair body of PoseGraphBuilder::processImages (pose_graph_builder.h:553-627) over a list of
+// (pair, path hypothesis) tuples, straight from the compact scene: createCorrespondenceMatrix (:553-565), the
+// in-traversal test of the hypothesis A* composed (graph_traversal.h:790 -> :194-233; 1.5 x threshold, 5 inliers,
+// pose_graph_builder.h:798-811), estimatePose with that hypothesis as the only guess if it passed (:616-627,
+// :940-1078).  Workers pull the next tuple from a shared counter — the reference's worker-pulls-queue structure
+// (:391-413; libgomp is absent in this image, so std::thread).  This is what bench.py's cpu_baseline /
+// --impl reference legs time and what --verify compares the GPU verdicts with.
+// out: testPassed[n], testCount[n], info[n x 8] = {success, branch, inlierNumber, pathInliers, votes0..3}, E[n x 9], qt[n x 7]
+int pgo_scene_pipeline_batch(uint64_t V, const double *focal, const double *size, const uint64_t *kpOffset, const float *kp,
+                             const uint32_t *pairViews, const uint64_t *mOffset, const uint32_t *matches, double thrPx,
+                             uint64_t minInliers, uint64_t nItems, const uint32_t *pairIds, const double *hyp,
+                             const uint8_t *hasHyp, int threads, uint8_t *testPassed, uint32_t *testCount, int64_t *info,
+                             double *E, double *qt)
+{
+    (void)V;
+    int used = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+    if (used < 1) used = 1;
+    if ((uint64_t)used > nItems) used = nItems ? (int)nItems : 1;
+    std::atomic<int64_t> next(0);
+    auto worker = [&]() {
+        std::vector<double> corr;
+        std::vector<uint8_t> mask;
+        for (;;) {
+            const int64_t i = next.fetch_add(1);  // queue pop under the mutex, pose_graph_builder.h:400-413
+            if (i >= (int64_t)nItems) break;
+            const uint32_t p = pairIds[i];
+            const uint32_t src = pairViews[2 * p], dst = pairViews[2 * p + 1];
+            const size_t n = (size_t)(mOffset[p + 1] - mOffset[p]);
+            corr.resize(n * 4);
+            double thrNorm = 0.0;
+            const double f = focal[src], cx = size[2 * src] / 2.0, cy = size[2 * src + 1] / 2.0;
+            createCorrespondenceMatrix(kp + 2 * kpOffset[src], kp + 2 * kpOffset[dst], matches + 2 * mOffset[p], n, f, f, cx, cy,
+                                       thrPx, corr.data(), thrNorm);
+            std::vector<SE3> poses;
+            testPassed[i] = 0;
+            testCount[i] = 0;
+            if (hasHyp[i]) {
+                const SE3 h = se3FromArray(hyp + 7 * i);
+                size_t cnt = 0;
+                const bool ok = inTraversalTest(corr.data(), n, h, 1.5 * thrNorm, 5, cnt);
+                testPassed[i] = ok;
+                testCount[i] = (uint32_t)cnt;
+                if (ok) poses.push_back(h);
+            }
+            mask.clear();
+            EstimateResult r = estimatePose(corr.data(), n, thrNorm, minInliers, poses.data(), poses.size(), mask);
+            std::memcpy(E + 9 * i, r.E, sizeof(r.E));
+            se3ToArray(r.pose, qt + 7 * i);
+            int64_t *o = info + 8 * i;
+            o[0] = r.success; o[1] = r.branch; o[2] = (int64_t)r.inlierNumber; o[3] = (int64_t)r.pathInliers;
+            for (int k = 0; k < 4; k++) o[4 + k] = (int64_t)r.votes[k];
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < used; t++) pool.emplace_back(worker);
+    worker();
+    for (auto &th : pool) th.join();
+    return used;
+}
+
 // ---- host loop -----------------------------------------------------------------------------------
 uint64_t pgo_pairlog_size() { return sizeof(host::PairLog); }
 
@@ -218,5 +278,27 @@ void pgo_run_stats(void *h, uint64_t *stats)
     stats[4] = r.skipped; stats[5] = r.corrEvals; stats[6] = r.fallbackRuns;
 }
 void pgo_run_free(void *h) { delete (PgoRun *)h; }
+
+// Replay a logged run through the sequential oracle host (host::replay).  out[6] = {checked, mismatches, edges,
+// searches, firstBad, firstBadField}
+void pgo_replay_scene(uint64_t V, const double *sim, uint64_t P, const uint32_t *pairViews, const uint64_t *mOffset,
+                      double simThreshold, uint64_t minPoints, uint64_t maxDepth, double weight, int usePathFinding,
+                      uint64_t maxPairs, uint64_t n, const uint32_t *src, const uint32_t *dst, const int64_t *pairIndex,
+                      const uint8_t *visible, const uint8_t *hadPath, const uint8_t *committed, const uint32_t *touched,
+                      const uint32_t *nCorr, const double *hyp, const double *q, const double *t, const double *score,
+                      int64_t *out)
+{
+    host::Scene sc;
+    sc.V = V; sc.sim = sim; sc.P = P; sc.pairViews = pairViews; sc.mOffset = mOffset;
+    host::Config cfg;
+    cfg.similarityThreshold = simThreshold; cfg.minimumPointNumber = minPoints; cfg.maximumSearchDepth = maxDepth;
+    cfg.traversalHeuristicsWeight = weight; cfg.usePathFinding = usePathFinding != 0;
+    host::ReplayLog lg;
+    lg.n = n; lg.src = src; lg.dst = dst; lg.pairIndex = pairIndex; lg.visible = visible; lg.hadPath = hadPath;
+    lg.committed = committed; lg.touchedNodes = touched; lg.nCorr = nCorr; lg.hyp = hyp; lg.q = q; lg.t = t; lg.score = score;
+    const host::ReplayResult r = host::replay(sc, cfg, lg, maxPairs);
+    out[0] = (int64_t)r.checked; out[1] = (int64_t)r.mismatches; out[2] = (int64_t)r.edges; out[3] = (int64_t)r.searches;
+    out[4] = r.firstBad; out[5] = r.firstBadField;
+}
 
 }  // extern "C"

@@ -14,6 +14,7 @@
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <cstring>
 #include <map>
 #include <queue>
 #include <set>
@@ -350,6 +351,84 @@ inline RunResult run(const Scene &sc, const Config &cfg, size_t maxPairs = 0)
         if (er.branch == 1) out.pathAccepted++; else out.fallbackAccepted++;
         out.log.push_back(lg);
     }
+    return out;
+}
+
+// ---- replay of a logged run (bench.py --verify, tests/test_gpu_fullsize.py) ------------------------------------
+// The product logs, per queue position, what its speculative-wave host decided: visibility, the hypothesis its A*
+// composed, the touched-node count, and the verdict the engine returned.  `replay` walks the queue with THIS file's
+// sequential host — same PoseGraph / VisibilityTable / aStar as run() — but takes the per-pair verdict from the log
+// instead of computing it (the verdicts themselves are checked separately, tuple by tuple, against estimatePose), and
+// compares everything the host logic produces on the way: queue order, duplicate skips, hasLink, whether a path was
+// found, the composed pose bit for bit, touched nodes.  A run whose log passes both checks committed exactly the graph
+// the sequential reference semantics commit.
+struct ReplayLog {
+    size_t n = 0;
+    const uint32_t *src = nullptr, *dst = nullptr;
+    const int64_t *pairIndex = nullptr;
+    const uint8_t *visible = nullptr, *hadPath = nullptr, *committed = nullptr;
+    const uint32_t *touchedNodes = nullptr, *nCorr = nullptr;
+    const double *hyp = nullptr;    // n x 7 (q xyzw, t): the hypothesis handed to the engine (valid if hadPath)
+    const double *q = nullptr, *t = nullptr, *score = nullptr;  // committed edge (valid if committed)
+};
+struct ReplayResult {
+    size_t checked = 0, mismatches = 0, edges = 0, searches = 0;
+    int64_t firstBad = -1;
+    int firstBadField = 0;  // 1 queue order, 2 skip, 3 visible, 4 hadPath, 5 touched, 6 hypothesis, 7 length
+};
+
+inline ReplayResult replay(const Scene &sc, const Config &cfg, const ReplayLog &lg, size_t maxPairs = 0)
+{
+    ReplayResult out;
+    PoseGraph graph;
+    VisibilityTable vis;
+    auto queue = buildPairQueue(sc, cfg.similarityThreshold);
+    auto bad = [&](size_t k, int field) {
+        ++out.mismatches;
+        if (out.firstBad < 0) { out.firstBad = (int64_t)k; out.firstBadField = field; }
+    };
+    size_t k = 0;
+    while (!queue.empty()) {
+        if (maxPairs && k >= maxPairs) break;
+        if (k >= lg.n) { bad(k, 7); break; }
+        const auto vp = queue.top();
+        queue.pop();
+        const ViewId src = std::get<1>(vp), dst = std::get<2>(vp);
+        const size_t pos = k++;
+        ++out.checked;
+        if (lg.src[pos] != src || lg.dst[pos] != dst) { bad(pos, 1); break; }
+        const bool dup = graph.hasEdge(src, dst) || graph.hasEdge(dst, src);  // :438-443
+        if (dup) {
+            if (lg.committed[pos]) bad(pos, 2);
+            continue;
+        }
+        const bool visible = vis.hasLink(src, dst);  // :456-457
+        if ((lg.visible[pos] != 0) != visible) bad(pos, 3);
+        const size_t n = lg.pairIndex[pos] >= 0 ? lg.nCorr[pos] : 0;
+        if (n < cfg.minimumPointNumber) {  // :550-551
+            if (lg.committed[pos]) bad(pos, 2);
+            continue;
+        }
+        if (cfg.usePathFinding && visible) {  // :569-603
+            AStarResult ar = aStar(graph, sc, src, dst, cfg.maximumSearchDepth, cfg.traversalHeuristicsWeight);
+            ++out.searches;
+            if ((lg.hadPath[pos] != 0) != ar.pathFound) bad(pos, 4);
+            if (lg.touchedNodes[pos] != (uint32_t)ar.touchedNodes) bad(pos, 5);
+            if (ar.pathFound && lg.hadPath[pos]) {
+                const double h[7] = {ar.pose.q.x, ar.pose.q.y, ar.pose.q.z, ar.pose.q.w, ar.pose.t.x, ar.pose.t.y, ar.pose.t.z};
+                if (std::memcmp(h, lg.hyp + 7 * pos, sizeof h) != 0) bad(pos, 6);
+            }
+        } else if (lg.hadPath[pos])
+            bad(pos, 4);
+        if (!lg.committed[pos]) continue;  // :641-642
+        Edge e{src, dst, SE3{Quat{lg.q[4 * pos], lg.q[4 * pos + 1], lg.q[4 * pos + 2], lg.q[4 * pos + 3]},
+                             Vec3{lg.t[3 * pos], lg.t[3 * pos + 1], lg.t[3 * pos + 2]}},
+               lg.score[pos]};
+        graph.addEdge(src, dst, e);  // :649-654
+        vis.addLink(src, dst);       // :692
+        ++out.edges;
+    }
+    if (!maxPairs && k != lg.n) bad(k, 7);
     return out;
 }
 

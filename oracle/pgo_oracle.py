@@ -315,3 +315,53 @@ def run_scene(scene, sim_threshold=0.0, thr_px=0.4, min_inliers=20, min_points=5
     L.pgo_run_free(h)
     keys = ["edges", "path_accepted", "fallback_accepted", "rejected", "skipped", "corr_evals", "fallback_runs"]
     return log, dict(zip(keys, (int(s) for s in stats)))
+
+
+def scene_pipeline_batch(scene, pair_ids, hyp, has_hyp, thr_px=0.4, min_inliers=20, threads=0):
+    """Per-pair body of processImages (createCorrespondenceMatrix -> in-traversal test -> estimatePose) over
+    (pair, hypothesis) tuples, worker-pulls-queue on `threads` host threads (0 = all)."""
+    L = lib()
+    focal = _d(scene["focal"]); size = _d(scene["size"])
+    kpo = np.ascontiguousarray(scene["kp_offset"], dtype=np.uint64)
+    kp = np.ascontiguousarray(scene["kp"], dtype=np.float32)
+    pv = np.ascontiguousarray(scene["pair_views"], dtype=np.uint32)
+    mo = np.ascontiguousarray(scene["m_offset"], dtype=np.uint64)
+    mt = np.ascontiguousarray(scene["matches"], dtype=np.uint32)
+    ids = np.ascontiguousarray(pair_ids, dtype=np.uint32)
+    n = len(ids)
+    hyp = _d(np.asarray(hyp, dtype=np.float64).reshape(n, 7))
+    has = np.ascontiguousarray(has_hyp, dtype=np.uint8)
+    tp, tc = np.zeros(n, dtype=np.uint8), np.zeros(n, dtype=np.uint32)
+    info = np.zeros((n, 8), dtype=np.int64)
+    E, qt = np.zeros((n, 9)), np.zeros((n, 7))
+    L.pgo_scene_pipeline_batch.restype = C.c_int
+    used = L.pgo_scene_pipeline_batch(C.c_uint64(len(focal)), _p(focal, _dp), _p(size, _dp), _p(kpo, _u64p), _p(kp, _fp),
+                                      _p(pv, _u32p), _p(mo, _u64p), _p(mt, _u32p), C.c_double(thr_px), C.c_uint64(min_inliers),
+                                      C.c_uint64(n), _p(ids, _u32p), _p(hyp, _dp), _p(has, _u8p), C.c_int(threads),
+                                      _p(tp, _u8p), _p(tc, _u32p), _p(info, _i64p), _p(E, _dp), _p(qt, _dp))
+    return dict(test_passed=tp, test_count=tc, info=info, E=E, pose=qt, threads=int(used))
+
+
+def replay_scene(scene, log, sim_threshold=0.0, min_points=50, max_depth=5, weight=0.8, use_path_finding=True, max_pairs=0):
+    """Walk the queue with the sequential oracle host, taking the verdicts from a product log (builder.LOG_DTYPE
+    records incl. `hyp`) and comparing the host-side decisions.  Returns dict(checked, mismatches, edges, searches,
+    first_bad, first_bad_field)."""
+    L = lib()
+    sim = _d(scene["sim"])
+    pv = np.ascontiguousarray(scene["pair_views"], dtype=np.uint32)
+    mo = np.ascontiguousarray(scene["m_offset"], dtype=np.uint64)
+    f = {k: np.ascontiguousarray(log[k]) for k in ("src", "dst", "pairIndex", "visible", "hadPath", "committed", "touchedNodes",
+                                                    "nCorr", "hyp", "q", "t", "score")}
+    out = np.zeros(6, dtype=np.int64)
+    L.pgo_replay_scene.restype = None
+    L.pgo_replay_scene(C.c_uint64(len(sim)), _p(sim, _dp), C.c_uint64(len(pv)), _p(pv, _u32p), _p(mo, _u64p),
+                       C.c_double(sim_threshold), C.c_uint64(min_points), C.c_uint64(max_depth), C.c_double(weight),
+                       C.c_int(1 if use_path_finding else 0), C.c_uint64(max_pairs), C.c_uint64(len(log)),
+                       _p(f["src"].astype(np.uint32), _u32p), _p(f["dst"].astype(np.uint32), _u32p),
+                       _p(f["pairIndex"].astype(np.int64), _i64p), _p(f["visible"].astype(np.uint8), _u8p),
+                       _p(f["hadPath"].astype(np.uint8), _u8p), _p(f["committed"].astype(np.uint8), _u8p),
+                       _p(f["touchedNodes"].astype(np.uint32), _u32p), _p(f["nCorr"].astype(np.uint32), _u32p),
+                       _p(_d(f["hyp"]), _dp), _p(_d(f["q"]), _dp), _p(_d(f["t"]), _dp), _p(_d(f["score"]), _dp),
+                       _p(out, _i64p))
+    keys = ["checked", "mismatches", "edges", "searches", "first_bad", "first_bad_field"]
+    return dict(zip(keys, (int(x) for x in out)))

@@ -12,6 +12,7 @@ NVLink on device buffers, gloo on CPU tensors in the tests) so that every rank r
 commit.  With world_size == 1 no collective is issued.
 """
 import ctypes as C
+import os
 import threading
 import time
 
@@ -30,7 +31,7 @@ LOG_DTYPE = np.dtype([("src", np.uint32), ("dst", np.uint32), ("pairIndex", np.i
                       ("hadPath", np.uint8), ("testPassed", np.uint8), ("branch", np.uint8), ("committed", np.uint8),
                       ("pad", np.uint8, (3,)), ("testCount", np.uint32), ("inlierNumber", np.uint32), ("nCorr", np.uint32),
                       ("touchedNodes", np.uint32), ("E", np.float64, (9,)), ("q", np.float64, (4,)),
-                      ("t", np.float64, (3,)), ("score", np.float64)], align=True)
+                      ("t", np.float64, (3,)), ("score", np.float64), ("hyp", np.float64, (7,))], align=True)
 
 
 class PgbConfig(C.Structure):
@@ -53,7 +54,7 @@ class PgbCounters(C.Structure):
 
 
 RECORD_DTYPE = np.dtype([("valid", np.uint8), ("has_hyp", np.uint8), ("has_path_verdict", np.uint8), ("final_is_path", np.uint8),
-                         ("touched", np.uint32), ("v", VERDICT_DTYPE)], align=True)
+                         ("touched", np.uint32), ("v", VERDICT_DTYPE), ("hyp", np.float64, (7,))], align=True)
 WAVE_DONE, WAVE_NEED_GPU, WAVE_NEED_EXCHANGE = 0, 1, 2
 
 PGB_EXPORTS = ["pgb_create", "pgb_destroy", "pgb_remaining", "pgb_set_fallback_verdicts", "pgb_set_fallback_verdicts_some",
@@ -385,7 +386,7 @@ class PoseGraphBuilder:
         # several ranks: the Python loop below, because the record exchange goes through torch.distributed
         self.native_loop = bool(native_loop)
         # speculative A* searches of a wave round as one batched device call (K6) instead of the host thread pool
-        self.gpu_search = bool(gpu_search)
+        self.gpu_search = bool(gpu_search) and os.environ.get("PGI_GPU_SEARCH", "1") != "0"
         self.gpu_search_min_batch = int(gpu_search_min_batch)
         self.prefetch_streams = int(prefetch_streams)
         self.timing = {}

@@ -823,6 +823,7 @@ int32_t searchOnDevice(pgb_builder *b, const std::vector<uint32_t> &todo)
             searchPosition(b, k, b->scratch[0]);
             std::vector<uint32_t> expHost = it.expanded;
             std::sort(exp.begin(), exp.end());
+            exp.erase(std::unique(exp.begin(), exp.end()), exp.end());  // (a position redone on the host lists re-expansions)
             std::sort(expHost.begin(), expHost.end());
             expHost.erase(std::unique(expHost.begin(), expHost.end()), expHost.end());
             const bool same = hasHyp == it.hasHyp && (!hasHyp || !memcmp(&hyp, &it.hyp, sizeof(SE3))) && touched == it.touched &&
@@ -908,6 +909,7 @@ void commitPosition(pgb_builder *b, Item &it)
     const pgi_verdict *final = it.finalV;
     lg.had_path = it.hasHyp;
     lg.touched_nodes = it.touched;
+    if (it.hasHyp) { memcpy(lg.hyp, it.hyp.q, 32); memcpy(lg.hyp + 4, it.hyp.t, 24); }
     if (it.pathV) { lg.test_passed = it.pathV->test_passed; lg.test_count = it.pathV->test_count; }
     lg.branch = final->accepted ? final->branch : 0;
     lg.inlier_number = final->inlier_count;
@@ -1283,6 +1285,7 @@ void pgb_export_records(pgb_builder *b, pgb_record *out)
         r.final_is_path = (it.pathV && it.finalV == it.pathV) ? 1 : 0;
         r.touched = it.touched;
         if (it.pathV) r.v = *it.pathV;
+        if (it.hasHyp) { memcpy(r.hyp, it.hyp.q, 32); memcpy(r.hyp + 4, it.hyp.t, 24); }
     }
 }
 
@@ -1296,6 +1299,8 @@ uint32_t pgb_import_records(pgb_builder *b, const pgb_record *in)
         const pgb_record &r = in[k];
         it.remoteKnown = r.valid != 0;
         it.hasHyp = r.has_hyp != 0;
+        memcpy(it.hyp.q, r.hyp, 32);
+        memcpy(it.hyp.t, r.hyp + 4, 24);
         it.touched = r.touched;
         it.pathV = it.finalV = nullptr;
         if (r.has_path_verdict) { it.remoteV = r.v; it.pathV = &it.remoteV; }

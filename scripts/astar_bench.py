@@ -15,7 +15,12 @@ from pose_graph_initialization_b200 import builder as B  # noqa: E402
 
 views, wave, maxpos = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 mode = sys.argv[4] if len(sys.argv) > 4 else "gpu"
-sc = dense_scene(views, seed=1)
+import fake_verdicts  # noqa: E402
+
+ring = os.environ.get("RING", "1") != "0"  # similarity structure of the benchmark scenes
+if ring:
+    fake_verdicts.FB_SCORE[:] = [0.35, 0.10]  # fallback inlier ratio of the 40 %-outlier scenes
+sc = dense_scene(views, seed=3, ring_cameras=ring)
 cfg = dict(similarity_threshold=0.0, minimum_inlier_number=20, minimum_point_number=50, maximum_search_depth=5,
            traversal_heuristics_weight=0.8, use_path_finding=True)
 if mode == "check":

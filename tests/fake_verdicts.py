@@ -25,6 +25,9 @@ def _unit_pose(h):
     return out
 
 
+FB_SCORE = [0.55, 0.10]  # fallback inlier ratio: base, spread (module-level knob of the benchmark script)
+
+
 def fake_verdicts(items, n_corr, path_ratio=3, fallback=True):
     """items: ITEM_DTYPE records with need_gpu set.  fallback=True (lazy-fallback waves): a failed/absent path
     hypothesis runs the fallback (status bit 0), whose verdict depends on the pair alone.  fallback=False (prefetched
@@ -48,7 +51,7 @@ def fake_verdicts(items, n_corr, path_ratio=3, fallback=True):
     v["accepted"] = 1
     v["branch"] = np.where(path_ok, 1, 2)
     inl_path = n_corr - (hh % np.uint64(max(1, n_corr // 100))).astype(np.uint32)
-    inl_fb = (0.55 * n_corr + (hp % np.uint64(max(1, n_corr // 10)))).astype(np.uint32)
+    inl_fb = (FB_SCORE[0] * n_corr + (hp % np.uint64(max(1, int(n_corr * FB_SCORE[1]))))).astype(np.uint32)
     v["inlier_count"] = np.where(path_ok, inl_path, inl_fb)
     v["path_inliers"] = np.where(path_ok, inl_path, 0)
     v["status"] = np.where(path_ok, 0, 1)
@@ -64,8 +67,17 @@ def fake_verdicts(items, n_corr, path_ratio=3, fallback=True):
     return v
 
 
-def dense_scene(n_views, n_corr=2000, seed=0, decimals=3):
-    """A host-only scene (similarities + pair list, no keypoints): every i<j pair queued."""
+def dense_scene(n_views, n_corr=2000, seed=0, decimals=3, ring_cameras=False):
+    """A host-only scene (similarities + pair list, no keypoints): every i<j pair queued.  ring_cameras=True takes the
+    similarity matrix of the benchmark scenes' generator (scene.make_scene: cosine of the viewing directions of
+    cameras on a ring, half of the pairs at 0)."""
+    if ring_cameras:
+        from pose_graph_initialization_b200 import scene as S
+
+        sc = S.make_scene(n_views=n_views, n_corr=1, seed=seed, n_points=64)
+        pv = sc["pair_views"]
+        mo = (np.arange(len(pv) + 1, dtype=np.uint64) * np.uint64(n_corr))
+        return dict(sim=sc["sim"], pair_views=pv, m_offset=mo, focal=sc["focal"])
     rng = np.random.default_rng(seed)
     ang = rng.uniform(0, 2 * np.pi, n_views)
     d = np.abs(ang[:, None] - ang[None, :])

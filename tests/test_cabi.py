@@ -35,7 +35,8 @@ def test_struct_layouts_match_the_header():
     from pose_graph_initialization_b200 import builder, engine
 
     assert engine.VERDICT_DTYPE.itemsize == 160  # pgi_verdict, also the all-gather element
-    assert builder.ITEM_DTYPE.itemsize == 72 and builder.EDGE_DTYPE.itemsize == 88 and builder.LOG_DTYPE.itemsize == 176
+    assert builder.ITEM_DTYPE.itemsize == 72 and builder.EDGE_DTYPE.itemsize == 88 and builder.LOG_DTYPE.itemsize == 232
+    assert builder.RECORD_DTYPE.itemsize == 224 and engine.ADJ_ENTRY_DTYPE.itemsize == 24 and engine.SEARCH_RESULT_DTYPE.itemsize == 32
 
 
 def test_no_cpu_fallback_without_a_device():
