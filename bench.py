@@ -1,15 +1,19 @@
 #!/usr/bin/env python
-"""bench.py — pairs verified/s of the B200 hypothesis-verification path on BASELINE.json's configs[1]
-(synthetic 300-view scene, 44,850 pairs, 2,000 correspondences/pair, 30 % outliers).
+"""bench.py — pairs verified/s of the B200 hypothesis-verification path.  Default workload: BASELINE.json's
+configs[2], the configuration its target is quoted on (synthetic 1,000-view scene, 499,500 pairs, 2,000
+correspondences/pair, 40 % outliers, 32 GB of FP64 correspondences: fits one B200).
 
-A "step" is one complete pass of the hot path over the scene: every queued pair goes through A* (host),
-in-traversal test + getInliers + five-point + E->(R,t) vote or the robust fallback (GPU), and the
-sequential commit, producing the pose graph.  `value` times the step with the correspondences already built
-in HBM (registration outside the timed region); `e2e` times the same step through the public API from HOST
-buffers (pinned-size H2D of the compact scene + on-device createCorrespondenceMatrix inside the timed region,
-verdicts read back every wave).
+A "step" is one complete pass of the hot path over the scene: every queued pair goes through A* (K6 on the device,
+small rounds on the host pool), in-traversal test + getInliers + five-point + E->(R,t) vote or the robust fallback
+(K1-K5), and the sequential commit, producing the pose graph.  Every step runs prepare() — H2D of the compact scene
+from PINNED host buffers + on-device createCorrespondenceMatrix — and then run():
+  e2e    = the K (prepare + run) steps back to back, bracketed by barrier + synchronize (copies inside);
+  value  = the K run() regions alone (inputs resident in HBM when each region starts), each bracketed by
+           barrier + synchronize, summed.
+CUDA events on the device, max over ranks.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config cfg2_300v]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config cfg3_1000v]
+                    [--verify N] [--dump-tuples FILE]
 """
 import argparse
 import json
@@ -27,6 +31,9 @@ sys.path.insert(0, ROOT)
 
 # ncu --set full on k5_fallback_score (profiles/): (dram__bytes_read + dram__bytes_write) / pairs of the launch
 NCU_K5_DRAM_BYTES_PER_PAIR_LAUNCH = 164_500
+# FP64 operations of one minimal five-point solve (K4a + K4b + K4c), counted by instrumenting the oracle's solver
+# (tests/test_oracle_properties.py::test_five_point_flop_count keeps the figure honest): see DESIGN.md section 3
+K4_FLOPS_PER_SOLVE = 60_000.0
 
 
 def load_peaks():
@@ -94,30 +101,60 @@ def scene_outlier_ratio(name):
     return S.CONFIGS.get(name, {}).get("outlier_ratio")
 
 
-def dense_sample(scene, pair_ids, thr_px=0.4):
-    from pose_graph_initialization_b200 import scene as S
-    corr, thr, off = [], [], [0]
-    for p in pair_ids:
-        c, t = S.pair_correspondences(scene, int(p), thr_px)
-        corr.append(c); thr.append(t); off.append(off[-1] + len(c))
-    return np.vstack(corr), np.array(off, dtype=np.uint64), np.array(thr)
+def config_keys(name, scene):
+    """The workload description both arms print (identical keys and values)."""
+    return {"workload": name, "views": int(len(scene["focal"])), "pairs": int(len(scene["pair_views"])),
+            "corr_per_pair": int(scene["m_offset"][1] - scene["m_offset"][0]), "outlier_ratio": scene_outlier_ratio(name)}
 
 
-def cpu_leg(scene, n_pairs, threads=0, seed=0):
-    """The oracle (CPU restatement of the reference path: estimatePose = fallback + E->(R,t) vote, the branch the
-    synthetic scenes take for >90 % of the pairs) on a bounded, evenly spaced sample of the scene's pairs, all
-    host threads.  Only place besides tests/ and smoke() where oracle/ is executed."""
+# ---- (pair, hypothesis) tuples: what the CPU legs replay ------------------------------------------------------
+def tuple_fixture(name):
+    return os.path.join(ROOT, "tests", "golden", "tuples_%s.npz" % name)
+
+
+def tuples_from_log(log, n):
+    """n evenly spaced queue positions that went through the per-pair pipeline, as (pair, hypothesis) tuples."""
+    from pose_graph_initialization_b200.verify import verifiable_positions
+    pos = verifiable_positions(log)
+    if len(pos) > n:
+        pos = pos[np.unique(np.linspace(0, len(pos) - 1, n).astype(np.int64))]
+    lg = log[pos]
+    return dict(position=pos.astype(np.int64), pair_id=lg["pairIndex"].astype(np.uint32), has_hyp=lg["hadPath"].astype(np.uint8),
+                hyp=np.ascontiguousarray(lg["hyp"]), branch=lg["branch"].astype(np.uint8), committed=lg["committed"].astype(np.uint8),
+                inlier_number=lg["inlierNumber"].astype(np.uint32), test_passed=lg["testPassed"].astype(np.uint8))
+
+
+def load_tuples(name, scene):
+    """Committed fixture of the config (written by `bench.py --dump-tuples` on a B200): evenly spaced queue positions
+    of the sequential run with the hypothesis A* composed for each.  Without a fixture the pairs are replayed without
+    hypothesis (every pair takes the fallback: a slower CPU arm; the line says so)."""
+    path = tuple_fixture(name)
+    if os.path.exists(path):
+        d = np.load(path)
+        return {k: d[k] for k in d.files}, "fixture tests/golden/%s (logged hypotheses of the sequential run)" % os.path.basename(path)
+    P = len(scene["pair_views"])
+    ids = np.unique(np.linspace(0, P - 1, min(P, 8192)).astype(np.int64)).astype(np.uint32)
+    return dict(pair_id=ids, has_hyp=np.zeros(len(ids), dtype=np.uint8), hyp=np.zeros((len(ids), 7))), \
+        "no tuple fixture for this config: every pair replayed without hypothesis (fallback branch only)"
+
+
+def cpu_pipeline(scene, tup, sel, threads=0):
+    """The oracle's per-pair pipeline (createCorrespondenceMatrix -> in-traversal test -> estimatePose: path branch or
+    robust fallback -> E->(R,t) vote), worker-pulls-queue on all host threads, over the tuples `sel`.
+    Only place besides tests/ and smoke() where oracle/ is executed."""
     from oracle import pgo_oracle as O
     O.build()
-    P = len(scene["pair_views"])
-    ids = np.unique(np.linspace(0, P - 1, n_pairs).astype(np.int64))
-    corr, off, thr = dense_sample(scene, ids)
     t0 = time.perf_counter()
-    r = O.estimate_pose_batch(corr, off, thr, np.zeros((len(ids), 7)), np.zeros(len(ids), dtype=np.uint8), 20, threads)
+    r = O.scene_pipeline_batch(scene, tup["pair_id"][sel], tup["hyp"][sel], tup["has_hyp"][sel], 0.4, 20, threads)
     dt = time.perf_counter() - t0
-    acc = int(r["info"][:, 0].sum())
-    return dict(pairs=len(ids), seconds=dt, pairs_per_s=len(ids) / dt, cores=int(r["threads"]), accepted=acc,
-                corr=int(off[-1]))
+    info = r["info"]
+    return dict(pairs=int(len(sel)), seconds=dt, pairs_per_s=len(sel) / dt, cores=int(r["threads"]),
+                path=int(((info[:, 0] > 0) & (info[:, 1] == 1)).sum()), fallback=int(((info[:, 0] > 0) & (info[:, 1] == 2)).sum()),
+                rejected=int((info[:, 0] == 0).sum()))
+
+
+CPU_NOTE = ("per-pair pipeline of processImages (PGB:553-627) on logged (pair, hypothesis) tuples; A* (~0.5 ms per pair on a "
+            "host thread, <2 % of the per-pair CPU time) and the commit are not replayed")
 
 
 def _cv2_usac_one(job):
@@ -170,28 +207,33 @@ def cv2_yardstick_child(path, workers):
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU path (oracle port: the reference cannot be compiled in this image)
-    timed on the host cores.  Rank 0 only."""
+    timed on the host cores, all threads, on the same workload's tuple mix.  Rank 0 only."""
     if rank != 0:
         return
     scene = make_scene(args.config)
     cores = os.cpu_count() or 1
-    sample = args.cpu_sample or 128 * cores  # ~5 s of all-core CPU work per step
-    for _ in range(args.warmup):
-        cpu_leg(scene, max(cores, 8))
-    tot_p, tot_s, last = 0, 0.0, None
-    for _ in range(args.steps):
-        last = cpu_leg(scene, sample)
+    tup, src = load_tuples(args.config, scene)
+    n = len(tup["pair_id"])
+    sample = min(n, args.cpu_sample or 128 * cores)  # ~4-8 s of all-core CPU work per step
+    for w in range(args.warmup):
+        cpu_pipeline(scene, tup, np.arange(w * cores, w * cores + cores) % n)
+    tot_p, tot_s, last, mix = 0, 0.0, None, {"path": 0, "fallback": 0, "rejected": 0}
+    for k in range(args.steps):
+        # a different bounded slice of the evenly spaced tuples every step (stride keeps each slice evenly spaced)
+        stride = max(1, n // sample)
+        sel = (k + stride * np.arange(sample)) % n
+        last = cpu_pipeline(scene, tup, sel)
         tot_p += last["pairs"]; tot_s += last["seconds"]
+        for key in mix:
+            mix[key] += last[key]
     v = tot_p / tot_s
     line = {
         "impl": "reference", "metric": "image_pairs_verified_per_sec", "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / max(args.steps, 1), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.config, "views": int(len(scene["focal"])), "pairs": int(len(scene["pair_views"])),
-                   "corr_per_pair": int(scene["m_offset"][1] - scene["m_offset"][0])},
+        "config": config_keys(args.config, scene),
         "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": last["cores"], "kind": "port",
-                         "sample": f"{sample} evenly spaced pairs of the scene per step, estimatePose (fallback + E->(R,t) vote), "
-                                   f"{last['cores']} std::thread workers"},
+                         "sample": "%d tuples per step, %s; %s; branch mix of the timed tuples %s" % (sample, src, CPU_NOTE, mix)},
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -206,6 +248,24 @@ def emit(line):
 _REAL_STDOUT = 1
 
 
+def verify_run(scene, log, n_tuples, replay_pairs):
+    """--verify: the finished run against the CPU oracle at benchmark scale (pose_graph_initialization_b200/verify.py)."""
+    from oracle import pgo_oracle as O
+    from pose_graph_initialization_b200.verify import compare_tuples, verifiable_positions
+    O.build()
+    pos = verifiable_positions(log)
+    if n_tuples > 0 and len(pos) > n_tuples:
+        pos = pos[np.unique(np.linspace(0, len(pos) - 1, n_tuples).astype(np.int64))]
+    tup = compare_tuples(O, scene, log, pos)
+    t0 = time.perf_counter()
+    rep = O.replay_scene(scene, log, max_pairs=replay_pairs)
+    rep["seconds"] = time.perf_counter() - t0
+    return {"tuples": tup, "host_replay": rep, "ok": tup["mismatches"] == 0 and rep["mismatches"] == 0,
+            "what": "tuples: logged (pair, hypothesis) tuples through the oracle's per-pair pipeline, verdicts compared bit for bit; "
+                    "host_replay: the oracle's sequential host (own queue, visibility table, A*) fed the logged verdicts, every "
+                    "host-side decision and composed hypothesis compared (max_pairs=%d, 0 = whole queue)" % replay_pairs}
+
+
 def main():
     global _REAL_STDOUT
     # keep stdout clean for the one-line contract: everything else this process (or NCCL) prints goes to stderr
@@ -217,24 +277,29 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--config", default="cfg2_300v")
-    ap.add_argument("--wave", type=int, default=0, help="queue positions per speculative wave (0 = 256 on one GPU, 512 with several ranks: every round of a wave costs a record exchange there)")
+    ap.add_argument("--config", default="cfg3_1000v")
+    ap.add_argument("--wave", type=int, default=0, help="queue positions per speculative wave (0 = default of the config)")
     ap.add_argument("--window", type=int, default=0, help="host re-search window (0 = library default)")
     ap.add_argument("--no-overlap", action="store_true", help="prefetch the fallback before the waves instead of concurrently")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the cpu_baseline sample (0 = 256 x cores, ~10-15 s)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="tuples in the cpu_baseline sample (0 = 256 x cores, ~10 s)")
     ap.add_argument("--fb-wave", type=int, default=1024, help="pairs per fallback prefetch wave")
     ap.add_argument("--fb-streams", type=int, default=2, help="background contexts running prefetch waves concurrently")
     ap.add_argument("--cv2-yardstick", default="", help=argparse.SUPPRESS)
     ap.add_argument("--workers", type=int, default=1, help=argparse.SUPPRESS)
     ap.add_argument("--lazy", action="store_true", help="run the fallback lazily inside the waves instead of prefetching it")
+    ap.add_argument("--host-search", action="store_true", help="A* on the host thread pool instead of the device (K6)")
+    ap.add_argument("--search-min-batch", type=int, default=16, help="rounds with fewer searches stay on the host pool")
+    ap.add_argument("--verify", type=int, default=-1, help="after the timed steps, check the last run against the CPU oracle: "
+                    "N evenly spaced tuples (0 = every pair) + sequential host replay; exit code 3 on any mismatch")
+    ap.add_argument("--verify-replay", type=int, default=-1, help="queue positions replayed by the oracle host (-1 = whole queue up to 400 views, else 20000; 0 = whole queue)")
+    ap.add_argument("--dump-tuples", default="", help="write N evenly spaced (pair, hypothesis) tuples of the last run (npz)")
+    ap.add_argument("--dump-n", type=int, default=8192)
     args = ap.parse_args()
     if args.cv2_yardstick:  # child mode of cv2_yardstick(): no torch, no CUDA
         sys.exit(cv2_yardstick_child(args.cv2_yardstick, args.workers))
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.wave <= 0:
-        args.wave = 256 if world == 1 else 512
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
@@ -259,7 +324,9 @@ def main():
         torch.cuda.synchronize()
 
     scene = make_scene(args.config)  # same seed on every rank => identical scene
-    # the step's host inputs live in PINNED memory (the e2e leg copies them host->device every step)
+    if args.wave <= 0:
+        args.wave = B.default_wave_size(len(scene["focal"]), world, not args.host_search)
+    # the step's host inputs live in PINNED memory (every step copies them host->device)
     for key in ("matches", "kp", "sim", "pair_views", "m_offset", "kp_offset", "focal", "size"):
         src = np.ascontiguousarray(scene[key])
         pinned = torch.empty(src.nbytes, dtype=torch.uint8, pin_memory=True).numpy().view(src.dtype).reshape(src.shape)
@@ -268,87 +335,75 @@ def main():
     P = len(scene["pair_views"])
     n_corr = int(scene["m_offset"][1] - scene["m_offset"][0])
     pgb = B.PoseGraphBuilder(kCoreNumber_=max(1, (os.cpu_count() or 1) // world),  # ranks share the box's cores
-                              kSimilarityThreshold_=0.0, scene=scene, device=local_rank,
-                             wave_size=args.wave, prefetch_fallback=not args.lazy, overlap_fallback=not args.no_overlap, research_window=args.window, fallback_wave=args.fb_wave, prefetch_streams=args.fb_streams, group=group, rank=rank,
-                             world_size=world)
+                             kSimilarityThreshold_=0.0, scene=scene, device=local_rank, wave_size=args.wave,
+                             prefetch_fallback=not args.lazy, overlap_fallback=not args.no_overlap, research_window=args.window,
+                             fallback_wave=args.fb_wave, prefetch_streams=args.fb_streams, gpu_search=not args.host_search,
+                             gpu_search_min_batch=args.search_min_batch, group=group, rank=rank, world_size=world)
     pgb.prepare()
     fp64_peak = pgb.engine.fp64_peak(fused=False)
     fp64_peak_fma = pgb.engine.fp64_peak(fused=True)
 
-    # ---- `value`: inputs resident in HBM (registration done once, outside the timed region) -------------------
     for _ in range(args.warmup):
         pgb.run()
     pgb.reset_engine_stats()
     sampler = ClockSampler(local_rank)
+    K = max(args.steps, 1)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    step_wall = {"e2e": [], "detail": []}
     barrier()
     sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
     t0 = time.perf_counter()
-    counters = None
-    step_wall = {"resident": [], "e2e": []}
-    for _ in range(args.steps):
+    counters, timing, search_stats = None, None, None
+    for k in range(K):
         ts = time.perf_counter()
-        graph = pgb.run()
-        step_wall["resident"].append(round((time.perf_counter() - ts) * 1e3, 1))
-        counters = pgb.counters
-    barrier()
-    ev1.record()
-    ev1.synchronize()
+        evs[k][0].record()
+        pgb.prepare()          # H2D of the compact scene from pinned host buffers + K0 (synchronous)
+        barrier()
+        evs[k][1].record()
+        tp = time.perf_counter()
+        graph = pgb.run()      # inputs resident in HBM from here on
+        n_edges = graph.numEdges()
+        barrier()
+        evs[k][2].record()
+        step_wall["e2e"].append(round((time.perf_counter() - ts) * 1e3, 1))
+        step_wall["detail"].append({"prepare_ms": round((tp - ts) * 1e3, 1),
+                                    **{kk: round(v * 1e3, 1) for kk, v in pgb.timing.items() if kk.endswith("_s")}})
+        counters, timing, search_stats = pgb.counters, dict(pgb.timing), dict(getattr(pgb, "search_stats", {}) or {})
+    torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
-    ms_resident = ev0.elapsed_time(ev1)
+    ms_e2e = evs[0][0].elapsed_time(evs[K - 1][2])
+    ms_resident = sum(evs[k][1].elapsed_time(evs[k][2]) for k in range(K))
     st = pgb.engine_stats()
-    timing = dict(pgb.timing)
-
-    # ---- `e2e`: same step from host buffers through the public API (register_scene H2D + K0 inside) -----------
-    pgb.reset_engine_stats()
-    barrier()
-    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev2.record()
-    for _ in range(args.steps):
-        ts = time.perf_counter()
-        pgb.prepare()
-        tp = time.perf_counter()
-        graph = pgb.run()
-        n_edges = graph.numEdges()
-        step_wall["e2e"].append(round((time.perf_counter() - ts) * 1e3, 1))
-        step_wall.setdefault("e2e_detail", []).append(
-            {"prepare_ms": round((tp - ts) * 1e3, 1), **{k: round(v * 1e3, 1) for k, v in pgb.timing.items() if k.endswith("_s")}})
-    barrier()
-    ev3.record()
-    ev3.synchronize()
-    ms_e2e = ev2.elapsed_time(ev3)
-    st_e2e = pgb.engine_stats()
+    log = pgb.log
 
     t = torch.tensor([ms_resident, ms_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_resident, ms_e2e = float(t[0]), float(t[1])
-    K = max(args.steps, 1)
     value = P * K / (ms_resident * 1e-3)
     e2e = P * K / (ms_e2e * 1e-3)
 
     # ---- K1 on full-size waves (HBM roofline probe): every local pair scored against one hypothesis ---------------
-    # In the pipeline K1 only sees the few hundred hypotheses of a round (launch-latency bound); its bandwidth
-    # behaviour is measured here on waves of 8192 pairs x 2000 rows (0.5 GB each, inputs larger than L2).
+    # In the pipeline K1 only sees the hypotheses of a round (launch-latency bound); its bandwidth behaviour is measured
+    # here on waves of 8192 pairs x 2000 rows (0.5 GB each, inputs larger than L2), at most 64 waves.
     eng = pgb.engine
     n_local = eng.n_pairs
+    n_probe = min(n_local, 64 * 8192)
     ident = np.tile(np.array([0.0, 0.0, 0.0, 1.0, 1.0, 0.0, 0.0]), (8192, 1))
     def k1_pass():
-        for s0 in range(0, n_local, 8192):
-            ids = np.arange(s0, min(n_local, s0 + 8192), dtype=np.uint32)
+        for s0 in range(0, n_probe, 8192):
+            ids = np.arange(s0, min(n_probe, s0 + 8192), dtype=np.uint32)
             eng.run_wave(ids, np.arange(len(ids) + 1, dtype=np.uint32), ident[:len(ids)], flags=B.WAVE_PATH)
     k1_pass()
     eng.reset_stats()
     k1_pass()
     st_k1 = eng.stats()
 
-    # ---- K5/K4 on one fallback wave with nothing else on the GPU: in the step three contexts overlap (wave loop + two
-    # prefetch streams), so the per-stage CUDA-event brackets there contain each other's kernels; the roofline's launch
-    # durations are taken from this isolated wave of the same pairs instead (same launches: 8 x (K4, K5) + K3).
-    # (1776 pairs = 4 x 148 SMs x 3 resident K5 CTAs: the grid is a whole number of resident waves, as the two prefetch
-    # streams of the step fill each other's partial waves)
+    # ---- the fallback kernels on one wave with nothing else on the GPU: in the step several contexts overlap (wave loop,
+    # two prefetch streams), so per-stage CUDA-event brackets there contain each other's kernels; the roofline's launch
+    # durations — and the choice of the dominant kernel — come from this isolated wave of the same pairs (same launches:
+    # 8 x (K4a, K4b, K4c, K5) + K3).  1776 pairs = 4 x 148 SMs x 3 resident K5 CTAs.
     fb_ids = np.arange(min(n_local, 1776), dtype=np.uint32)
     eng.run_wave(fb_ids, None, None, flags=B.WAVE_FALLBACK)
     eng.reset_stats()
@@ -358,12 +413,13 @@ def main():
     fb_iters = {"pairs": int(len(it)), "mean": float(it.mean()), "p10": int(it[len(it) // 10]), "median": int(it[len(it) // 2]),
                 "p90": int(it[(len(it) * 9) // 10]), "max": int(it[-1]),
                 "models_per_pair": st_fb["fallback_models"] / max(1, st_fb["fallback_pairs"])}
+    iso = {"k4_fallback_solve": st_fb["ms_fallback_solve"], "k5_fallback_score": st_fb["ms_fallback_score"],
+           "k3_decompose_vote": st_fb["ms_decompose"]}
+    dominant = max(iso, key=iso.get)
 
-    # ---- roofline of the dominant kernel (per-stage CUDA-event times from the engine's own stream) -----------
     stages = {"k1_score_hypotheses": st["ms_score"], "k2_fivept_first_solution": st["ms_fivept"],
               "k4_fallback_solve": st["ms_fallback_solve"], "k5_fallback_score": st["ms_fallback_score"],
-              "k3_decompose_vote": st["ms_decompose"]}
-    dominant = max(stages, key=stages.get)
+              "k3_decompose_vote": st["ms_decompose"], "k6_astar_search": float(search_stats.get("ms_search", 0.0)) * 1.0}
     hbm_peak, hbm_src = load_peaks()
     # K5: every scored model evaluates the Sampson residual of all N correspondences: 33 FP64 flops each (algorithmic)
     k5_flops = st_fb["fallback_models"] * n_corr * 33.0
@@ -371,71 +427,93 @@ def main():
     k5_launches = 8
     roof_k5 = {"kernel": "k5_fallback_score", "bound": "fp64", "achieved": k5_flops / k5_t / 1e12 if k5_t > 0 else 0.0,
                "peak": fp64_peak, "unit": "TFLOP/s",
-               # dram__bytes_read+write per launch from profiles/ (ncu --set full, 1184 pairs x 125 iterations): ~195 MB;
-               # algorithmic bytes per launch = pairs x N x 32 B read once
                "traffic": NCU_K5_DRAM_BYTES_PER_PAIR_LAUNCH * len(fb_ids),
                # FP64 rows staged once per CTA + the (72 B FP64 + 48 B FP32) model records of the chunk's iterations
                "algorithmic_bytes_per_launch": int(len(fb_ids) * (
                    n_corr * 32 + 120.0 * st_fb["fallback_models"] / max(1, st_fb["fallback_pairs"] * 8))),
                "launches": k5_launches, "ms_per_launch": st_fb["ms_fallback_score"] / k5_launches,
-               "timed_on": "one isolated %d-pair fallback wave after the timed region (in the step three contexts overlap and "
+               "timed_on": "one isolated %d-pair fallback wave after the timed region (in the step several contexts overlap and "
                            "their CUDA-event brackets contain each other's kernels)" % len(fb_ids),
-               "peak_source": "measured live: DMUL+DADD chains (parity forbids FMA); DFMA peak %.1f TFLOP/s; "
-                              "achieved counts 33 algorithmic FP64 flops per model x correspondence evaluation, most of "
-                              "which are certified in FP32 (see DESIGN.md section 3)" % fp64_peak_fma}
+               "peak_source": "measured live by pgi_dbg_fp64_peak: non-fused DMUL+DADD chains %.2f TFLOP/s (parity forbids FMA), "
+                              "DFMA chains %.2f TFLOP/s; not in MEASURED_PEAKS.json.  `achieved` counts 33 algorithmic FP64 flops "
+                              "per model x correspondence evaluation, most of which are certified in FP32 (DESIGN.md section 3)"
+                              % (fp64_peak, fp64_peak_fma),
+               "fp64_peak_nonfused_tflops": fp64_peak, "fp64_peak_dfma_tflops": fp64_peak_fma}
     roof_k5["frac"] = roof_k5["achieved"] / fp64_peak if fp64_peak > 0 else None
+    k4_solves = float(st_fb["fallback_pairs"]) * float(it.mean())
+    roof_k4 = {"kernel": "k4_fallback_solve", "bound": "fp64", "unit": "TFLOP/s", "peak": fp64_peak,
+               "achieved": k4_solves * K4_FLOPS_PER_SOLVE / max(st_fb["ms_fallback_solve"] * 1e-3, 1e-9) / 1e12,
+               "traffic": None, "launches": 24, "ms_per_launch": st_fb["ms_fallback_solve"] / 24,
+               "timed_on": roof_k5["timed_on"], "peak_source": roof_k5["peak_source"],
+               "flops_per_solve": K4_FLOPS_PER_SOLVE}
+    roof_k4["frac"] = roof_k4["achieved"] / fp64_peak if fp64_peak > 0 else None
     # K1: 32 B per hypothesis x correspondence evaluation, measured on the full-size probe waves above
     k1_bytes = st_k1["corr_evals"] * 32.0
     k1_t = st_k1["ms_score"] * 1e-3
     roof_k1 = {"kernel": "k1_score_hypotheses", "bound": "hbm", "achieved": k1_bytes / k1_t / 1e9 if k1_t > 0 else 0.0,
                "peak": hbm_peak, "unit": "GB/s", "traffic": None,
-               "peak_source": hbm_src + " (MEASURED_PEAKS.json hbm_gbs); probe: %d pairs x %d rows per pass, waves of 8192 pairs" % (n_local, n_corr),
+               "peak_source": hbm_src + " (MEASURED_PEAKS.json hbm_gbs); probe: %d pairs x %d rows per pass, waves of 8192 pairs" % (n_probe, n_corr),
                "gcorr_evals_per_s": st_k1["corr_evals"] / k1_t / 1e9 if k1_t > 0 else 0.0}
     roof_k1["frac"] = roof_k1["achieved"] / hbm_peak
-    roofline = dict(roof_k5 if dominant in ("k5_fallback_score", "k4_fallback_solve") else roof_k1)
-    roofline["share_of_gpu_time"] = stages[dominant] / max(sum(stages.values()), 1e-9)
-    roofline["dominant"] = dominant
+    roofline = dict(roof_k5 if dominant == "k5_fallback_score" else roof_k4 if dominant == "k4_fallback_solve" else roof_k5)
+    roofline["dominant"] = roofline["kernel"]
+    roofline["share_of_isolated_fallback_wave"] = iso[roofline["kernel"]] / max(sum(iso.values()), 1e-9)
 
-    line = None
+    verify = None
+    if args.verify >= 0 and rank == 0:
+        replay = args.verify_replay if args.verify_replay >= 0 else (0 if len(scene["focal"]) <= 400 else 20000)
+        verify = verify_run(scene, log, args.verify, replay)
+    if args.dump_tuples and rank == 0:
+        np.savez_compressed(args.dump_tuples, **tuples_from_log(log, args.dump_n))
+
     if rank == 0:
         cores = os.cpu_count() or 1
-        cpu = cpu_leg(scene, args.cpu_sample or 256 * cores)  # ~10-15 s of all-core CPU work
+        tup = tuples_from_log(log, args.cpu_sample or 256 * cores)  # ~10 s of all-core CPU work
+        cpu = cpu_pipeline(scene, tup, np.arange(len(tup["pair_id"])))
         yard = cv2_yardstick(scene, 8 * cores, cores)  # ~1-2 s
         line = {
             "metric": "image_pairs_verified_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_resident / K, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.config, "views": int(len(scene["focal"])), "pairs": int(P), "corr_per_pair": n_corr,
-                       "outlier_ratio": scene_outlier_ratio(args.config), "wave": args.wave, "fallback": "lazy" if args.lazy else "prefetched",
+            "config": {**config_keys(args.config, scene), "wave": args.wave, "fallback": "lazy" if args.lazy else "prefetched",
+                       "search": "host pool" if args.host_search else "device (K6), rounds below %d searches on the host pool" % args.search_min_batch,
                        "l2": "inputs (%.1f GB of FP64 correspondences) larger than the 126 MB L2" % (P * n_corr * 32 / 1e9),
-                       "parallelism": "pairs sharded over %d rank(s), verdict all-gather" % world},
+                       "parallelism": "pairs sharded over %d rank(s), verdict exchange per wave round" % world},
+            "timing": "e2e: K x (prepare + run) back to back; value: the K run() regions (inputs resident), each bracketed by "
+                      "barrier + synchronize; CUDA events, max over ranks",
             "step_wall_ms": step_wall,
             "e2e": {"value": e2e, "unit": "pairs/s", "ms_per_step": ms_e2e / K,
-                    "h2d_bytes_per_step": int(st_e2e["h2d_bytes"] // K), "d2h_bytes_per_step": int(st_e2e["d2h_bytes"] // K)},
-            "gpu_launches": int(st["launches"]),
+                    "h2d_bytes_per_step": int((st["h2d_bytes"] + search_stats.get("h2d_bytes", 0) * K) // K),
+                    "d2h_bytes_per_step": int((st["d2h_bytes"] + search_stats.get("d2h_bytes", 0) * K) // K)},
+            "gpu_launches": int(st["launches"] + search_stats.get("launches", 0) * K),
             "gcorr_evals_per_sec": {"path_hypotheses": st["corr_evals"] / (ms_resident * 1e-3) / 1e9,
                                     "fallback_models": st["fallback_models"] * n_corr / (ms_resident * 1e-3) / 1e9},
-            "roofline": roofline, "roofline_k1_scoring": roof_k1, "roofline_k5_fallback": roof_k5,
-            "gpu_stage_ms_per_step": {k: v / K for k, v in stages.items()},
+            "roofline": roofline, "roofline_k1_scoring": roof_k1, "roofline_k5_fallback": roof_k5, "roofline_k4_fallback": roof_k4,
+            "gpu_stage_ms_per_step": {k: v / K for k, v in stages.items() if k != "k6_astar_search"} | {"k6_astar_search": stages["k6_astar_search"]},
             "gpu_stage_ms_note": "CUDA-event brackets per context; with the prefetch overlapping the waves the brackets of "
                                  "concurrent contexts include each other's kernels (sums exceed the step's GPU time)",
-            "gpu_stage_ms_isolated_fallback_wave": {"pairs": int(len(fb_ids)), "k4_fallback_solve": st_fb["ms_fallback_solve"],
-                                                    "k5_fallback_score": st_fb["ms_fallback_score"],
-                                                    "k3_decompose_vote": st_fb["ms_decompose"]},
+            "gpu_stage_ms_isolated_fallback_wave": {"pairs": int(len(fb_ids)), **iso},
             "host_s_per_step": {k: timing.get(k) for k in ("prefetch_s", "waves_s", "total_s", "engine_s", "exchange_s", "host_s",
                                                             "wait_prefetch_s", "engine_rounds", "exchanges")},
-            "search_stats": getattr(pgb, "search_stats", None), "host_counters": counters, "edges": int(n_edges), "wall_s_resident": wall,
+            "search_stats_last_step": search_stats,
+            "host_counters": counters, "edges": int(n_edges), "wall_s": wall,
+            "branch_mix": {k: int(counters[k]) for k in ("path_accepted", "fallback_accepted", "rejected", "skipped")},
             "cpu_baseline": {"value": cpu["pairs_per_s"], "unit": "pairs/s", "cores": cpu["cores"], "kind": "port",
-                             "sample": "%d evenly spaced pairs of the same scene through the oracle's estimatePose "
-                                       "(fallback + E->(R,t) vote), %.1f s" % (cpu["pairs"], cpu["seconds"]),
+                             "sample": "%d evenly spaced (pair, hypothesis) tuples of this run's log, %.1f s; %s; branch mix of the "
+                                       "sample: %d path / %d fallback / %d rejected"
+                                       % (cpu["pairs"], cpu["seconds"], CPU_NOTE, cpu["path"], cpu["fallback"], cpu["rejected"]),
                              "third_party_yardstick": yard},
             "fallback_iterations": fb_iters,
             "clocks": clocks,
         }
+        if verify is not None:
+            line["verify"] = verify
         emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if verify is not None and not verify["ok"]:
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -197,8 +197,8 @@ pgi_status pgi_graph_init(pgi_ctx *ctx, uint32_t n_views, const double *sim_to_n
 /* Write edge-list entries and set the per-vertex counts (both arrays have n_views entries; total >= committed). */
 pgi_status pgi_graph_apply(pgi_ctx *ctx, uint32_t n_entries, const pgi_adj_entry *entries,
                            const uint32_t *committed_count, const uint32_t *total_count);
-/* Run n searches.  expanded_bits receives n x ceil(V/32) words: bit v set iff vertex v's edge list was read
- * (graph_traversal.h:814-817).  Synchronous. max_depth <= 7. */
+/* Run n searches.  expanded_bits receives n x ceil(V/32) words: bit v set iff vertex v's edge list was iterated
+ * (expanded below the maximum depth, graph_traversal.h:814-822).  Synchronous. max_depth <= 7. */
 pgi_status pgi_graph_search(pgi_ctx *ctx, uint32_t n, const pgi_query *queries, uint32_t max_depth, double weight,
                             pgi_search_result *results, uint32_t *expanded_bits);
 pgi_status pgi_graph_stats(pgi_ctx *ctx, pgi_search_stats *out, int32_t reset);

@@ -318,6 +318,15 @@ class RecordExchanger:
         return self.np_out[:n].copy().view(RECORD_DTYPE)
 
 
+def default_wave_size(n_views, world_size=1, gpu_search=True):
+    """Queue positions per speculative wave.  Host-pool searches: 256 on one GPU (fewest re-searches), 512 with several
+    ranks (every round of a wave costs a record exchange).  Device searches (K6) are cheap in bulk and a round costs
+    a kernel round trip, so waves are larger (measured on cfg2/cfg3, scripts/gpu_r2_b.sh)."""
+    if not gpu_search:
+        return 256 if world_size == 1 else 512
+    return 1024 if n_views < 600 else 2048
+
+
 class PoseGraph:
     """Result container: committed edges in commit order (pose_graph.h:62-106)."""
 
@@ -369,7 +378,8 @@ class PoseGraphBuilder:
         self.device = device
         # measured on cfg2 (scripts/gpu_sweep.sh): 256 positions per wave is the optimum on one GPU (fewer A* re-searches
         # per position, rounds are cheap); with several ranks every round also costs a record exchange
-        self.wave_size = wave_size if wave_size else (256 if world_size == 1 else 512)
+        use_gpu_search = bool(gpu_search) and os.environ.get("PGI_GPU_SEARCH", "1") != "0"
+        self.wave_size = wave_size if wave_size else default_wave_size(len(scene["focal"]), world_size, use_gpu_search)
         self.prefetch_fallback = prefetch_fallback
         self.fallback_wave = fallback_wave
         self.group, self.rank, self.world = group, rank, world_size

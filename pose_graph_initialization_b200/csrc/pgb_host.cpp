@@ -369,7 +369,9 @@ void aStar(const GraphView &gv, const double *sim /*transposed*/, uint32_t V, ui
             continue;
         }
         S.mark[v] = epoch;  // nodeStates[v] = Open  :814
-        out.expanded.push_back(v);
+        // `expanded` = the vertices whose edge lists this search ITERATED (:820-866): what a later graph change must touch
+        // to invalidate the result.  A node popped at the maximum depth is marked but pushes nothing.
+        if (node.depth < maxDepth) out.expanded.push_back(v);
         const std::vector<Adj> &real = g.byVertex[v];
         const std::vector<OvAdj> *ovl = gv.ov ? &gv.ov->byVertex[v] : nullptr;
         const bool hasOv = ovl && !ovl->empty() && (*ovl)[0].pos < gv.cutoff;

@@ -106,7 +106,7 @@ struct pgi_ctx {
     pgi_search_result *h_results = nullptr;
     uint32_t *h_expBits = nullptr;
     uint32_t hApplyCap = 0, hQueryCap = 0;
-    int popLookahead = 1;
+    int popLookahead = 1, stagedPush = 1;
     cudaEvent_t evS0 = nullptr, evS1 = nullptr;
     pgi_search_stats sstats;
 };
@@ -779,6 +779,7 @@ pgi_status pgi_graph_init(pgi_ctx *ctx, uint32_t n_views, const double *sim_to_n
     slotsPerSm = (slotsPerSm / kAstarWarps) * kAstarWarps;
     if (const char *e = getenv("PGI_ASTAR_HEAP")) heapCap = (uint32_t)std::max(1024, atoi(e));
     if (const char *e = getenv("PGI_ASTAR_POP")) ctx->popLookahead = atoi(e) != 0;
+    if (const char *e = getenv("PGI_ASTAR_STAGED")) ctx->stagedPush = atoi(e) != 0;
     if (!heapCap) {
         const uint64_t want = (uint64_t)V * V / 2;
         heapCap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 65536), 1u << 20);
@@ -879,8 +880,10 @@ pgi_status pgi_graph_search(pgi_ctx *ctx, uint32_t n, const pgi_query *queries, 
     a.heaps = ctx->d_heaps; a.heapCap = ctx->heapCap; a.arenas = ctx->d_arenas; a.arenaCap = ctx->arenaCap;
     a.results = ctx->d_results; a.expandedBits = ctx->d_expBits; a.nextQuery = ctx->d_nextQuery;
     a.popLookahead = ctx->popLookahead;
+    a.staged = ctx->stagedPush;
     const uint32_t ctas = std::min<uint32_t>((n + kAstarWarps - 1) / kAstarWarps, ctx->searchSlots / kAstarWarps);
-    const size_t smem = (size_t)kAstarWarps * words * 4;
+    const size_t smem = (size_t)kAstarWarps * ((size_t)kStageItems * sizeof(HeapItemDev) + (size_t)kChunk * 2 + (size_t)2 * words * 4);
+    CK(cudaFuncSetAttribute(k6_astar_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
     CK(cudaEventRecord(ctx->evS0, s));
     k6_astar_search<<<ctas, kAstarWarps * 32, smem, s>>>(a);
     CK(cudaEventRecord(ctx->evS1, s));

@@ -75,6 +75,7 @@ struct SearchArgs {
     uint32_t *expandedBits;  // n x words
     uint32_t *nextQuery;     // work counter (zeroed before the launch)
     int popLookahead;        // 1: warp-cooperative pop (4 levels per round trip); 0: lane 0 walks alone
+    int staged;              // 1: expansions are replayed in shared memory (expandStaged); 0: directly on the heap in HBM
 };
 
 __device__ __forceinline__ HeapItemDev ldItem(const HeapItemDev *p)
@@ -218,11 +219,187 @@ __device__ inline void popHeapWarp(HeapItemDev *H, uint32_t hs, int lane)
     }
 }
 
+// ---- staged expansion -------------------------------------------------------------------------------------------
+// The sift-ups of an expansion are a chain of dependent heap accesses, and on the heap in HBM every link of the chain
+// is an L2 round trip.  So an expansion is replayed in shared memory, kChunk edge-list entries at a time:
+//   * the chunk's admissible children are appended to a staging buffer (slots hs .. hs + C - 1 of the heap);
+//   * the slots a sequential std::push_heap of those children can touch within kConeLevels levels — for level j the
+//     contiguous window ((hs+1) >> j) - 1 .. ((hs+kChunk) >> j) - 1 — are loaded next to them in ONE parallel round trip
+//     (the addresses depend on hs only, so the loads are issued together with the edge-list loads);
+//   * children not larger than their parent stay where they are (see the header); the others are replayed in list order
+//     by one lane on the staged copy (shared-memory latency), continuing in global memory in the rare case a child
+//     climbs past the staged levels;
+//   * new slots and touched windows are written back in parallel.
+// Heaps of up to kStageItems - kChunk slots are staged whole (every child replayed: parents may be new slots).
+constexpr int kChunk = 128;
+constexpr int kConeLevels = 6;
+constexpr int kStageItems = 416;  // >= kChunk + sum_j (kChunk/2^j + 2) = 266
+__device__ __forceinline__ int coneOff(int j)  // staging index of level j's window (j = 1..kConeLevels)
+{
+    // window sizes kChunk/2^j + 2 (66, 34, 18, 10, 6, 4): kChunk + sum_{k<j} (kChunk >> k) + 2 (j - 1)
+    return 2 * kChunk - (kChunk >> (j - 1)) + 2 * (j - 1);
+}
+__device__ __forceinline__ uint32_t coneStart(uint32_t hs, int j) { return ((hs + 1) >> j) - 1; }  // level-j ancestor of slot hs
+
+__device__ inline bool expandStaged(const SearchArgs &a, HeapItemDev *H, uint32_t &hs, uint32_t &pushes, const AdjDev *list,
+                                    uint32_t total, uint32_t nc, uint32_t cutoff, const uint32_t *bits, const double *simTo,
+                                    double c0, double c1, uint32_t ni, HeapItemDev *sStage, uint16_t *sList, int lane)
+{
+    const uint32_t ltMask = (1u << lane) - 1u;
+    for (uint32_t base = 0; base < total; base += kChunk) {
+        // ---- loads: 4 list entries per lane + the staging windows (all independent of each other)
+        AdjDev e[4];
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const uint32_t idx = base + 32u * b + lane;
+            if (idx < total) e[b] = list[idx];
+            else { e[b].score = 0.0; e[b].next = 0; e[b].tag = 0; }
+        }
+        const bool small = hs + kChunk <= (uint32_t)kStageItems;
+        if (small) {
+            for (uint32_t p = lane; p < hs; p += 32) stItem(sStage + p, ldItem(H + p));
+        } else {
+#pragma unroll
+            for (int j = 1; j <= kConeLevels; j++) {
+                const uint32_t count = ((hs + kChunk) >> j) - ((hs + 1) >> j) + 1;
+                const int off = coneOff(j);
+                for (uint32_t k = lane; k < count; k += 32) stItem(sStage + off + k, ldItem(H + coneStart(hs, j) + k));
+            }
+        }
+        // ---- evaluate the children (graph_traversal.h:830-862)
+        bool valid[4];
+        double f[4];
+        uint32_t next[4], m[4];
+        uint32_t hiddenAny = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const uint32_t idx = base + 32u * b + lane;
+            valid[b] = false;
+            f[b] = 0.0;
+            next[b] = 0;
+            bool hidden = false;
+            if (idx < total) {
+                if (idx >= nc && e[b].tag > cutoff)
+                    hidden = true;  // predicted by a later wave position: not part of this search's graph
+                else if (!(e[b].score < 0.0)) {  // kMinimumInlierRatio is `const bool` receiving 0.0 (:613, :839)
+                    next[b] = e[b].next;
+                    if (!((bits[next[b] >> 5] >> (next[b] & 31)) & 1u)) {  // nodeStates.find(next) == end  :855-856
+                        const double edgeCost = c0 > e[b].score ? e[b].score : c0;  // MIN :843
+                        const double h = simTo[next[b]];
+                        const double ntd = c1 < h ? h : c1;  // MAX :847
+                        f[b] = a.weight * edgeCost + a.oneMinusWeight * ntd;  // :851-852
+                        valid[b] = true;
+                    }
+                }
+            }
+            m[b] = __ballot_sync(0xffffffffu, valid[b]);
+            hiddenAny |= __ballot_sync(0xffffffffu, hidden);
+        }
+        const uint32_t C = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
+        if (C) {
+            if (hs + C > a.heapCap) return false;
+            uint32_t cIdx[4];
+            {
+                uint32_t acc = 0;
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    cIdx[b] = acc + __popc(m[b] & ltMask);
+                    acc += __popc(m[b]);
+                }
+            }
+            const uint32_t newBase = small ? hs : 0u;  // staging index of heap slot hs
+#pragma unroll
+            for (int b = 0; b < 4; b++)
+                if (valid[b]) {
+                    HeapItemDev it;
+                    it.f = f[b]; it.parent = ni; it.en = ((base + 32u * b + lane) << 16) | next[b];
+                    stItem(sStage + newBase + cIdx[b], it);
+                }
+            __syncwarp();
+            // ---- which children move at all (ordered list of their indices)
+            uint32_t nf = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                bool flag = false;
+                if (valid[b]) {
+                    if (small)
+                        flag = true;
+                    else {
+                        const uint32_t pp = (hs + cIdx[b] - 1) >> 1;
+                        flag = ldItem(sStage + coneOff(1) + (pp - coneStart(hs, 1))).f < f[b];
+                    }
+                }
+                const uint32_t bal = __ballot_sync(0xffffffffu, flag);
+                if (flag) sList[nf + __popc(bal & ltMask)] = (uint16_t)cIdx[b];
+                nf += __popc(bal);
+            }
+            __syncwarp();
+            // ---- replay std::push_heap for those children, in list order, on the staged copy
+            int maxLev = 0;
+            if (lane == 0) {
+                if (small) {
+                    for (uint32_t i = 0; i < nf; i++) {
+                        const uint32_t p0 = hs + sList[i];
+                        const HeapItemDev item = ldItem(sStage + p0);
+                        siftUp(sStage, p0, item);
+                    }
+                } else {
+                    for (uint32_t i = 0; i < nf; i++) {
+                        const uint32_t c = sList[i];
+                        const HeapItemDev item = ldItem(sStage + c);
+                        uint32_t p = hs + c;          // heap position of the hole
+                        HeapItemDev *holeAt = sStage + c;  // where the hole lives (staging buffer or the heap itself)
+                        int lev = 0;
+                        while (p > 0) {
+                            const uint32_t pp = (p - 1) >> 1;
+                            HeapItemDev *parAt = lev < kConeLevels ? sStage + coneOff(lev + 1) + (pp - coneStart(hs, lev + 1)) : H + pp;
+                            const HeapItemDev par = ldItem(parAt);
+                            if (!(par.f < item.f)) break;
+                            stItem(holeAt, par);
+                            holeAt = parAt;
+                            p = pp;
+                            ++lev;
+                        }
+                        stItem(holeAt, item);
+                        const int touched = lev < kConeLevels ? lev : kConeLevels;
+                        maxLev = maxLev < touched ? touched : maxLev;
+                    }
+                }
+            }
+            maxLev = __shfl_sync(0xffffffffu, maxLev, 0);
+            __syncwarp();
+            // ---- write back
+            if (small) {
+                for (uint32_t p = lane; p < hs + C; p += 32) stItem(H + p, ldItem(sStage + p));
+            } else {
+                for (uint32_t c = lane; c < C; c += 32) stItem(H + hs + c, ldItem(sStage + c));
+#pragma unroll
+                for (int j = 1; j <= kConeLevels; j++)
+                    if (j <= maxLev) {
+                        const uint32_t count = ((hs + kChunk) >> j) - ((hs + 1) >> j) + 1;
+                        const int off = coneOff(j);
+                        for (uint32_t k = lane; k < count; k += 32) stItem(H + coneStart(hs, j) + k, ldItem(sStage + off + k));
+                    }
+            }
+            hs += C;
+            pushes += C;
+        }
+        __syncwarp();
+        if (hiddenAny) break;  // predicted entries are in position order: everything behind is hidden too
+    }
+    return true;
+}
+
 __global__ void __launch_bounds__(kAstarWarps * 32) k6_astar_search(SearchArgs a)
 {
-    extern __shared__ uint32_t sBitsAll[];
+    extern __shared__ uint4 sDyn[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *bits = sBitsAll + (size_t)warp * a.words;
+    // per-warp shared memory: staging buffer of the expansion (kStageItems heap items), list of moving children, bit sets
+    HeapItemDev *sStage = reinterpret_cast<HeapItemDev *>(sDyn) + (size_t)warp * kStageItems;
+    uint16_t *sList = reinterpret_cast<uint16_t *>(reinterpret_cast<HeapItemDev *>(sDyn) + (size_t)kAstarWarps * kStageItems) + (size_t)warp * kChunk;
+    uint32_t *sBitsAll = reinterpret_cast<uint32_t *>(reinterpret_cast<uint16_t *>(reinterpret_cast<HeapItemDev *>(sDyn) + (size_t)kAstarWarps * kStageItems) + (size_t)kAstarWarps * kChunk);
+    uint32_t *bits = sBitsAll + (size_t)warp * 2 * a.words;  // expanded (blocks pushes)
+    uint32_t *rbits = bits + a.words;                         // expanded below the maximum depth: lists that were read
     const uint32_t slot = blockIdx.x * kAstarWarps + warp;
     HeapItemDev *H = a.heaps + (size_t)slot * a.heapCap;
     ArenaNodeDev *A = a.arenas + (size_t)slot * a.arenaCap;
@@ -234,7 +411,7 @@ __global__ void __launch_bounds__(kAstarWarps * 32) k6_astar_search(SearchArgs a
         if (qi >= a.n) break;
         const pgi_query q = a.queries[qi];
         const uint32_t from = q.src, to = q.dst, cutoff = q.cutoff;
-        for (uint32_t wI = lane; wI < a.words; wI += 32) bits[wI] = 0;
+        for (uint32_t wI = lane; wI < 2 * a.words; wI += 32) bits[wI] = 0;
         const double *simTo = a.simT + (size_t)to * a.V;
         uint32_t hs = 1, na = 0, touched = 0, pushes = 0, status = SEARCH_OK, found = 0, pathLen = 0;
         uint32_t path[8];
@@ -275,7 +452,10 @@ __global__ void __launch_bounds__(kAstarWarps * 32) k6_astar_search(SearchArgs a
                 found = 1;
                 break;  // exactly one path is tested (:792-800 with kMaximumPathNumber = 1)
             }
-            if (lane == 0) bits[v >> 5] |= 1u << (v & 31);  // nodeStates[v] = Open  :814
+            if (lane == 0) {
+                bits[v >> 5] |= 1u << (v & 31);  // nodeStates[v] = Open  :814
+                if (depth < a.maxDepth) rbits[v >> 5] |= 1u << (v & 31);  // edge list iterated below (:820)
+            }
             if (na >= a.arenaCap) { status = SEARCH_ARENA_OVERFLOW; break; }
             const uint32_t ni = na++;
             if (lane == 0) {
@@ -289,6 +469,9 @@ __global__ void __launch_bounds__(kAstarWarps * 32) k6_astar_search(SearchArgs a
             if (depth < a.maxDepth) {  // :820
                 const AdjDev *list = a.adj + (size_t)v * a.cap;
                 bool overflow = false;
+                if (a.staged) {
+                    overflow = !expandStaged(a, H, hs, pushes, list, total, nc, cutoff, bits, simTo, c0, c1, ni, sStage, sList, lane);
+                } else
                 for (uint32_t base = 0; base < total; base += 32) {
                     const uint32_t idx = base + lane;
                     bool valid = false, hidden = false;
@@ -351,7 +534,7 @@ __global__ void __launch_bounds__(kAstarWarps * 32) k6_astar_search(SearchArgs a
             r.pad = 0;
             a.results[qi] = r;
         }
-        for (uint32_t wI = lane; wI < a.words; wI += 32) a.expandedBits[(size_t)qi * a.words + wI] = bits[wI];
+        for (uint32_t wI = lane; wI < a.words; wI += 32) a.expandedBits[(size_t)qi * a.words + wI] = rbits[wI];
         __syncwarp();
     }
 }
