@@ -169,7 +169,7 @@ typedef struct pgi_adj_entry {
 typedef struct pgi_query {
     uint32_t src, dst; /* search from src to dst                                                    */
     uint32_t cutoff;   /* predicted entries with tag <= cutoff are part of the graph                */
-    uint32_t reserved;
+    uint32_t budget;   /* > 0: give up (status 4) once more than this many nodes were pushed         */
 } pgi_query;
 
 typedef struct pgi_search_result {
@@ -178,8 +178,8 @@ typedef struct pgi_search_result {
     uint16_t path[8];  /* vertices src .. dst of the tested path (path_len entries)                 */
     uint8_t found;     /* destination popped (graph_traversal.h:766)                                */
     uint8_t path_len;
-    uint8_t status;    /* 0 ok; 1 heap slab full, 2 arena full, 3 vertex without edge list: the caller repeats
-                          the search with its own (host) implementation                             */
+    uint8_t status;    /* 0 ok; 1 heap slab full, 2 arena full, 3 vertex without edge list, 4 push budget of the query
+                          exceeded: the caller repeats the search with its own (host) implementation   */
     uint8_t pad;
     uint32_t reserved;
 } pgi_search_result;

@@ -591,6 +591,10 @@ struct pgb_builder {
     int32_t searchError = 0;     // first engine status of a failed device search (surfaced by pgb_run_wave)
     bool gpuCheck = false;       // PGB_SEARCH_CHECK=1: every device search is repeated on the host and compared
     bool ovDirty = true;         // the overlay changed since it was last mirrored to the device
+    double hybridShare = 0.3;    // share of a round's estimated search work the host pool takes beside the device (0: none)
+    uint32_t gpuBudget = 0;      // push budget of the round's device queries (0: unlimited)
+    std::vector<uint32_t> srcCost;  // per source view: pushes of the last search that started there (cost estimate)
+    double meanCost = 0.0;       // running mean of pushes per search
     std::vector<pgi_adj_entry> gpuEntries, commitEntries;
     std::vector<uint32_t> gpuCommitted, gpuTotal, gpuBits, gpuTodo;
     std::vector<pgi_query> gpuQueries;
@@ -751,9 +755,10 @@ int32_t uploadOverlay(pgb_builder *b)
 
 // Search the positions of `todo` with the device backend (K6, pgi_graph_search); positions the device could not
 // finish (slab overflow) and trivially hypothesis-free positions are completed on the host.
-int32_t searchOnDevice(pgb_builder *b, const std::vector<uint32_t> &todo)
+int32_t searchOnDevice(pgb_builder *b, const std::vector<uint32_t> &todo, std::vector<uint32_t> &redo)
 {
     const double t0 = nowSec();
+    redo.clear();
     if (b->ovDirty) {
         const int32_t rc = uploadOverlay(b);
         if (rc != 0) return rc;
@@ -764,7 +769,7 @@ int32_t searchOnDevice(pgb_builder *b, const std::vector<uint32_t> &todo)
     for (uint32_t k : todo) {
         Item &it = b->wave[k];
         if (b->cfg.use_path_finding && it.visible && !it.staticSkip && !it.dupSkip) {  // pose_graph_builder.h:569-570
-            b->gpuQueries.push_back(pgi_query{it.src, it.dst, k, 0});
+            b->gpuQueries.push_back(pgi_query{it.src, it.dst, k, b->gpuBudget});
             b->gpuTodo.push_back(k);
         } else {
             it.hasHyp = false;
@@ -780,7 +785,6 @@ int32_t searchOnDevice(pgb_builder *b, const std::vector<uint32_t> &todo)
     const int32_t rc = b->gpuSearch(b->gpuEngine, n, b->gpuQueries.data(), (uint32_t)b->cfg.maximum_search_depth,
                                     b->cfg.traversal_heuristics_weight, b->gpuResults.data(), b->gpuBits.data());
     if (rc != 0) return rc;
-    std::vector<uint32_t> redo;
     for (uint32_t i = 0; i < n; i++) {
         const uint32_t k = b->gpuTodo[i];
         Item &it = b->wave[k];
@@ -812,33 +816,33 @@ int32_t searchOnDevice(pgb_builder *b, const std::vector<uint32_t> &todo)
     b->ctr.gpu_searches += n - redo.size();
     b->ctr.gpu_search_redo += redo.size();
     b->ctr.sec_search_gpu += nowSec() - t0;
-    if (!redo.empty()) searchOnHost(b, redo);
-    if (b->gpuCheck) {
-        // debug: repeat every device search on the host and compare what the wave logic consumes
-        for (uint32_t i = 0; i < n; i++) {
-            const uint32_t k = b->gpuTodo[i];
-            Item &it = b->wave[k];
-            const bool hasHyp = it.hasHyp;
-            const SE3 hyp = it.hyp;
-            std::vector<uint32_t> exp = it.expanded;
-            const uint32_t touched = it.touched, pushes = it.pushes;
-            searchPosition(b, k, b->scratch[0]);
-            std::vector<uint32_t> expHost = it.expanded;
-            std::sort(exp.begin(), exp.end());
-            exp.erase(std::unique(exp.begin(), exp.end()), exp.end());  // (a position redone on the host lists re-expansions)
-            std::sort(expHost.begin(), expHost.end());
-            expHost.erase(std::unique(expHost.begin(), expHost.end()), expHost.end());
-            const bool same = hasHyp == it.hasHyp && (!hasHyp || !memcmp(&hyp, &it.hyp, sizeof(SE3))) && touched == it.touched &&
-                              pushes == it.pushes && exp == expHost;
-            if (!same) {
-                if (b->ctr.search_mismatches < 10)
-                    fprintf(stderr, "[pgb] device/host search mismatch at wave position %u (%u -> %u): found %d/%d touched %u/%u pushes %u/%u expanded %zu/%zu\n",
-                            k, it.src, it.dst, (int)hasHyp, (int)it.hasHyp, touched, it.touched, pushes, it.pushes, exp.size(), expHost.size());
-                b->ctr.search_mismatches++;
-            }
+    return 0;
+}
+
+// PGB_SEARCH_CHECK=1: repeat every device search of the round on the host and compare what the wave logic consumes.
+void checkDeviceSearches(pgb_builder *b)
+{
+    for (uint32_t k : b->gpuTodo) {
+        Item &it = b->wave[k];
+        const bool hasHyp = it.hasHyp;
+        const SE3 hyp = it.hyp;
+        std::vector<uint32_t> exp = it.expanded;
+        const uint32_t touched = it.touched, pushes = it.pushes;
+        searchPosition(b, k, b->scratch[0]);
+        std::vector<uint32_t> expHost = it.expanded;
+        std::sort(exp.begin(), exp.end());
+        exp.erase(std::unique(exp.begin(), exp.end()), exp.end());  // (a position redone on the host lists re-expansions)
+        std::sort(expHost.begin(), expHost.end());
+        expHost.erase(std::unique(expHost.begin(), expHost.end()), expHost.end());
+        const bool same = hasHyp == it.hasHyp && (!hasHyp || !memcmp(&hyp, &it.hyp, sizeof(SE3))) && touched == it.touched &&
+                          pushes == it.pushes && exp == expHost;
+        if (!same) {
+            if (b->ctr.search_mismatches < 10)
+                fprintf(stderr, "[pgb] device/host search mismatch at wave position %u (%u -> %u): found %d/%d touched %u/%u pushes %u/%u expanded %zu/%zu\n",
+                        k, it.src, it.dst, (int)hasHyp, (int)it.hasHyp, touched, it.touched, pushes, it.pushes, exp.size(), expHost.size());
+            b->ctr.search_mismatches++;
         }
     }
-    return 0;
 }
 
 // Search the stale positions below `limit` (pgb_config.reserved can restrict the re-search to a window behind the
@@ -851,15 +855,82 @@ void searchStale(pgb_builder *b, uint32_t limit)
         if (b->wave[k].mine && !b->wave[k].searched) todo.push_back(k);
     bool done = false;
     if (b->gpuSearch && todo.size() >= b->gpuMinBatch && b->V <= 65535u && b->cfg.maximum_search_depth <= 7) {
-        const int32_t rc = searchOnDevice(b, todo);
-        if (rc == 0)
+        // Device and host pool work on the round together.  The device's time for a round is the time of its longest
+        // search (one warp per search), the pool's is the sum of its searches over the threads, so the pool takes the
+        // searches expected to be the longest — a position's previous search is the estimate — up to a share of the
+        // estimated work that is adapted round by round until both finish together.
+        std::vector<uint32_t> hostPart, devPart;
+        if (b->hybridShare > 0.0 && b->cfg.host_threads > 1) {
+            std::vector<std::pair<uint64_t, uint32_t>> est;
+            est.reserve(todo.size());
+            uint64_t total = 0;
+            if (b->srcCost.size() != b->V) b->srcCost.assign(b->V, 0);
+            const uint64_t typical = (uint64_t)std::max(1.0, b->meanCost);
+            for (uint32_t k : todo) {
+                // a position's previous search, else the last search from the same source view, else the running mean
+                const Item &it = b->wave[k];
+                const uint64_t c = it.pushes ? it.pushes : (b->srcCost[it.src] ? b->srcCost[it.src] : typical);
+                est.emplace_back(c, k);
+                total += c;
+            }
+            std::sort(est.begin(), est.end(), [](const auto &x, const auto &y) { return x.first != y.first ? x.first > y.first : x.second < y.second; });
+            const double budget = b->hybridShare * (double)total;
+            uint64_t acc = 0;
+            for (const auto &e : est) {
+                if ((double)acc < budget) { hostPart.push_back(e.second); acc += e.first; }
+                else devPart.push_back(e.second);
+            }
+            std::sort(devPart.begin(), devPart.end());
+            // the device gives up on a search that turns out more than twice as long as the longest one it was meant to
+            // get (and at least 4x the typical search): the pool repeats those few
+            const uint64_t longest = hostPart.size() < est.size() ? est[hostPart.size()].first : 0;  // est is sorted, longest first
+            b->gpuBudget = (uint32_t)std::min<uint64_t>(0x7fffffffu, std::max<uint64_t>(2 * longest, 4 * typical) + 4096);
+        } else {
+            devPart = todo;
+            b->gpuBudget = 0;
+        }
+        std::vector<uint32_t> redo;
+        int32_t rc = 0;
+        double tDev = 0.0, tHost = 0.0;
+        if (hostPart.empty()) {
+            const double t1 = nowSec();
+            rc = searchOnDevice(b, devPart, redo);
+            tDev = nowSec() - t1;
+        } else {
+            std::thread dev([&]() {
+                const double t1 = nowSec();
+                rc = searchOnDevice(b, devPart, redo);
+                tDev = nowSec() - t1;
+            });
+            const double t1 = nowSec();
+            searchOnHost(b, hostPart);
+            tHost = nowSec() - t1;
+            dev.join();
+            // move the share towards the point where both sides take the same time
+            if (tDev > 0.0 && tHost > 0.0) {
+                const double ratio = tDev / tHost;
+                const double step = ratio > 1.0 ? std::min(ratio, 1.25) : std::max(ratio, 0.8);
+                b->hybridShare = std::min(0.9, std::max(0.02, b->hybridShare * step));
+            }
+            b->ctr.sec_search_host_part += tHost;
+        }
+        if (rc == 0) {
+            if (!redo.empty()) searchOnHost(b, redo);
+            if (b->gpuCheck) checkDeviceSearches(b);
             done = true;
-        else {
+        } else {
             b->searchError = rc;
             fprintf(stderr, "[pgb] device search failed with status %d\n", (int)rc);
         }
     }
     if (!done) searchOnHost(b, todo);
+    if (b->srcCost.size() == b->V)
+        for (uint32_t k : todo) {
+            const Item &it = b->wave[k];
+            if (!it.pushes) continue;
+            b->srcCost[it.src] = it.pushes;
+            b->meanCost = b->meanCost > 0.0 ? 0.999 * b->meanCost + 0.001 * (double)it.pushes : (double)it.pushes;
+        }
     for (uint32_t k : todo) { b->ctr.astar_pops += b->wave[k].touched; b->ctr.astar_pushes += b->wave[k].pushes; }
     b->ctr.astar_runs += todo.size();
     if (b->rounds > 0) b->ctr.astar_reruns += todo.size();
@@ -1206,6 +1277,7 @@ int32_t pgb_set_search_backend(pgb_builder *b, pgb_graph_apply_fn apply, pgb_gra
     b->gpuMinBatch = min_batch;
     b->ovDirty = true;
     if (const char *e = getenv("PGB_SEARCH_CHECK")) b->gpuCheck = atoi(e) != 0;
+    if (const char *e = getenv("PGB_HYBRID_SHARE")) b->hybridShare = std::min(0.9, std::max(0.0, atof(e)));
     if (!apply) return 0;
     // bring the device graph up to the committed graph (normally empty at this point)
     std::vector<pgi_adj_entry> entries;

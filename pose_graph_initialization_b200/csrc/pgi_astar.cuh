@@ -54,7 +54,9 @@ enum : uint8_t {  // pgi_search_result.status
     SEARCH_OK = 0,
     SEARCH_HEAP_OVERFLOW = 1,   // the heap slab is too small: the caller repeats the search on the host
     SEARCH_ARENA_OVERFLOW = 2,
-    SEARCH_STALE_LIST = 3       // an expanded vertex without edge list (pose_graph.h:145-146 quirk): host repeats it
+    SEARCH_STALE_LIST = 3,      // an expanded vertex without edge list (pose_graph.h:145-146 quirk): host repeats it
+    SEARCH_BUDGET = 4           // more nodes pushed than the query's budget: the caller repeats it (a device round lasts as
+                                // long as its longest search, so the host keeps the rare very long ones for its thread pool)
 };
 
 struct SearchArgs {
@@ -410,7 +412,7 @@ __global__ void __launch_bounds__(kAstarWarps * 32) k6_astar_search(SearchArgs a
         qi = __shfl_sync(0xffffffffu, qi, 0);
         if (qi >= a.n) break;
         const pgi_query q = a.queries[qi];
-        const uint32_t from = q.src, to = q.dst, cutoff = q.cutoff;
+        const uint32_t from = q.src, to = q.dst, cutoff = q.cutoff, budget = q.budget;
         for (uint32_t wI = lane; wI < 2 * a.words; wI += 32) bits[wI] = 0;
         const double *simTo = a.simT + (size_t)to * a.V;
         uint32_t hs = 1, na = 0, touched = 0, pushes = 0, status = SEARCH_OK, found = 0, pathLen = 0;
@@ -517,6 +519,7 @@ __global__ void __launch_bounds__(kAstarWarps * 32) k6_astar_search(SearchArgs a
                     if (anyHidden) break;  // predicted entries are in position order: everything behind is hidden too
                 }
                 if (overflow) { status = SEARCH_HEAP_OVERFLOW; break; }
+                if (budget && pushes > budget) { status = SEARCH_BUDGET; break; }
             }
         }
         __syncwarp();

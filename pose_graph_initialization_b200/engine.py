@@ -90,7 +90,7 @@ def _f64(a):
 
 ADJ_ENTRY_DTYPE = np.dtype([("vertex", np.uint32), ("index", np.uint32), ("next", np.uint32), ("tag", np.uint32),
                             ("score", np.float64)], align=True)
-QUERY_DTYPE = np.dtype([("src", np.uint32), ("dst", np.uint32), ("cutoff", np.uint32), ("reserved", np.uint32)], align=True)
+QUERY_DTYPE = np.dtype([("src", np.uint32), ("dst", np.uint32), ("cutoff", np.uint32), ("budget", np.uint32)], align=True)
 SEARCH_RESULT_DTYPE = np.dtype([("touched", np.uint32), ("pushes", np.uint32), ("path", np.uint16, (8,)), ("found", np.uint8),
                                 ("path_len", np.uint8), ("status", np.uint8), ("pad", np.uint8), ("reserved", np.uint32)],
                                align=True)
