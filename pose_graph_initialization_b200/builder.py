@@ -388,6 +388,8 @@ class PoseGraphBuilder:
         # gloo group so that it never shares a communicator with the wave loop
         self.overlap = bool(overlap_fallback and prefetch_fallback)
         self.pf_group = None
+        self.pf_device = None
+        self.pf_stream = None
         self.engine = None
         self.engine_fb = None
         self.engine_fb2 = None
@@ -418,8 +420,14 @@ class PoseGraphBuilder:
                     self.engine_fb2 = _engine.Engine(device=self.device, min_inliers=self.min_inliers, background=True)
                 self.engine_fb2.share_pairs(self.engine)
             if self.world > 1 and self.pf_group is None:
+                # the prefetch worker thread gathers its chunks' verdicts over its OWN communicator (never shared with the
+                # wave loop's): NCCL over NVLink on device buffers when the job runs on GPUs, gloo in the CPU tests
+                import torch
                 import torch.distributed as dist
-                self.pf_group = dist.new_group(backend="gloo")
+                on_gpu = torch.cuda.is_available() and dist.get_backend() == "nccl"
+                self.pf_group = dist.new_group(backend="nccl" if on_gpu else "gloo")
+                self.pf_device = torch.device("cuda", self.device) if on_gpu else None
+                self.pf_stream = torch.cuda.Stream(device=self.pf_device) if on_gpu else None
 
     def engine_stats(self):
         st = self.engine.stats()
@@ -487,6 +495,9 @@ class PoseGraphBuilder:
 
             def prefetch_worker():
                 try:
+                    if self.pf_device is not None:
+                        import torch
+                        torch.cuda.set_device(self.pf_device)
                     chunk = self.fallback_wave * self.world
                     engines = [e for e in (self.engine_fb, self.engine_fb2) if e is not None]
                     pending = []  # submitted chunks, oldest first: one in flight per background engine
@@ -497,7 +508,12 @@ class PoseGraphBuilder:
                         v["pair_id"] = mine.astype(np.uint32)
                         if self.world > 1:  # every rank needs every pair's fallback verdict (predictions + commit)
                             counts = [int(np.count_nonzero(own == r)) for r in range(self.world)]
-                            parts = allgather_verdicts(v, counts, self.pf_group, None)
+                            if self.pf_device is not None:
+                                import torch
+                                with torch.cuda.stream(self.pf_stream):
+                                    parts = allgather_verdicts(v, counts, self.pf_group, self.pf_device)
+                            else:
+                                parts = allgather_verdicts(v, counts, self.pf_group, None)
                             merged = np.zeros(len(ids), dtype=VERDICT_DTYPE)
                             for r in range(self.world):
                                 merged[np.nonzero(own == r)[0]] = parts[r]

@@ -112,6 +112,33 @@ __device__ __forceinline__ void siftUp(HeapItemDev *H, uint32_t hole, const Heap
     stItem(H + hole, value);
 }
 
+// The same std::__push_heap by the whole warp, in one memory round trip whatever the depth.  The path from a slot to
+// the root is non-decreasing in f (heap property), so the ancestors smaller than `value` are the first L of the path:
+// lane j loads the j-th ancestor, a ballot yields L, ancestors 1..L each move one level down (lane j stores what it
+// loaded) and `value` lands on level L — exactly the moves of the sequential loop.  (A child that out-ranks most of a
+// 10^5-entry heap climbs ~15 levels; one lane walking them costs 15 dependent loads.)  All lanes pass the same
+// arguments; the caller separates consecutive calls with __syncwarp().
+__device__ __forceinline__ void siftUpWarp(HeapItemDev *H, uint32_t hole, const HeapItemDev &value, int lane)
+{
+    const uint32_t q = (hole + 1) >> lane;  // 1-based index of the lane-th ancestor (lane 0: the hole itself)
+    const bool have = lane >= 1 && q >= 1;
+    HeapItemDev anc;
+    anc.f = 0.0; anc.parent = 0; anc.en = 0;
+    if (have) anc = ldItem(H + q - 1);
+    const uint32_t smaller = __ballot_sync(0xffffffffu, have && anc.f < value.f);
+    const uint32_t L = (uint32_t)__ffs((int)~(smaller >> 1)) - 1u;  // consecutive set bits from bit 1 on
+    if (have && (uint32_t)lane <= L) stItem(H + (((hole + 1) >> (lane - 1)) - 1), anc);
+    if (lane == 0) stItem(H + (((hole + 1) >> L) - 1), value);
+}
+__device__ __forceinline__ HeapItemDev shflItem(const HeapItemDev &it, int src)
+{
+    HeapItemDev r;
+    r.f = __shfl_sync(0xffffffffu, it.f, src);
+    r.parent = __shfl_sync(0xffffffffu, it.parent, src);
+    r.en = __shfl_sync(0xffffffffu, it.en, src);
+    return r;
+}
+
 // std::pop_heap(H, H + hs) by one thread: __pop_heap -> __adjust_heap -> __push_heap.
 __device__ inline void popHeapSerial(HeapItemDev *H, uint32_t hs)
 {
@@ -210,15 +237,14 @@ __device__ inline void popHeapWarp(HeapItemDev *H, uint32_t hs, int lane)
         (void)steps;
     }
     __syncwarp();
-    if (lane == 0) {
-        uint32_t h = hole;
-        if ((len & 1u) == 0 && hole == (len - 2) / 2) {
-            const uint32_t second = 2 * (hole + 1);
-            stItem(H + h, ldItem(H + second - 1));
-            h = second - 1;
-        }
-        siftUp(H, h, value);
+    uint32_t h = hole;
+    if ((len & 1u) == 0 && hole == (len - 2) / 2) {  // warp-uniform
+        const uint32_t second = 2 * (hole + 1);
+        if (lane == 0) stItem(H + h, ldItem(H + second - 1));
+        h = second - 1;
+        __syncwarp();
     }
+    siftUpWarp(H, h, shflItem(value, 0), lane);
 }
 
 // ---- staged expansion -------------------------------------------------------------------------------------------
@@ -510,7 +536,7 @@ __global__ void __launch_bounds__(kAstarWarps * 32) k6_astar_search(SearchArgs a
                         while (fm) {
                             const int l = __ffs((int)fm) - 1;
                             fm &= fm - 1;
-                            if (lane == l) siftUp(H, pos, it);
+                            siftUpWarp(H, __shfl_sync(0xffffffffu, pos, l), shflItem(it, l), lane);
                             __syncwarp();
                         }
                         hs += cntv;
