@@ -181,7 +181,7 @@ typedef struct pgi_search_result {
     uint8_t status;    /* 0 ok; 1 heap slab full, 2 arena full, 3 vertex without edge list, 4 push budget of the query
                           exceeded: the caller repeats the search with its own (host) implementation   */
     uint8_t pad;
-    uint32_t reserved;
+    uint32_t kcycles;  /* SM clock cycles the search took on its warp, / 1024 (diagnostics)        */
 } pgi_search_result;
 
 typedef struct pgi_search_stats {
@@ -189,6 +189,8 @@ typedef struct pgi_search_stats {
     uint64_t launches;     /* K6 + apply kernels launched                                           */
     uint64_t queries, pops, pushes, overflows;
     uint64_t h2d_bytes, d2h_bytes;
+    uint64_t kcycles_sum;     /* sum over searches of their duration on the device (SM kilocycles)          */
+    uint64_t kcycles_longest; /* sum over launches of the longest search: what a launch lasts at least    */
 } pgi_search_stats;
 
 /* (Re)create the device graph for n_views vertices (<= 65535).  sim_to_next is the V x V similarity table already

@@ -899,11 +899,15 @@ pgi_status pgi_graph_search(pgi_ctx *ctx, uint32_t n, const pgi_query *queries, 
     st.ms_search += ms;
     st.launches += 1;
     st.queries += n;
+    uint32_t longest = 0;
     for (uint32_t i = 0; i < n; i++) {
         st.pops += results[i].touched;
         st.pushes += results[i].pushes;
         st.overflows += results[i].status != 0;
+        st.kcycles_sum += results[i].kcycles;
+        longest = std::max(longest, results[i].kcycles);
     }
+    st.kcycles_longest += longest;
     st.h2d_bytes += (uint64_t)n * sizeof(pgi_query);
     st.d2h_bytes += (uint64_t)n * (sizeof(pgi_search_result) + (uint64_t)words * 4);
     return PGI_OK;

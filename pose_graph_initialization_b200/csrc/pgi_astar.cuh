@@ -99,6 +99,14 @@ __device__ __forceinline__ void stItem(HeapItemDev *p, const HeapItemDev &it)
     *reinterpret_cast<uint4 *>(p) = v;
 }
 
+// Bring the cache line of *p into L1 (a real load: prefetch hints may be dropped).
+__device__ __forceinline__ void touchL1(const HeapItemDev *p)
+{
+    unsigned long long sink;
+    asm volatile("ld.global.ca.u64 %0, [%1];" : "=l"(sink) : "l"(p) : "memory");
+    (void)sink;
+}
+
 // std::__push_heap(first, hole, 0, value, less-on-f): libstdc++ bits/stl_heap.h
 __device__ __forceinline__ void siftUp(HeapItemDev *H, uint32_t hole, const HeapItemDev &value)
 {
@@ -437,6 +445,7 @@ __global__ void __launch_bounds__(kAstarWarps * 32) k6_astar_search(SearchArgs a
         if (lane == 0) qi = atomicAdd(a.nextQuery, 1u);
         qi = __shfl_sync(0xffffffffu, qi, 0);
         if (qi >= a.n) break;
+        const long long tStart = clock64();
         const pgi_query q = a.queries[qi];
         const uint32_t from = q.src, to = q.dst, cutoff = q.cutoff, budget = q.budget;
         for (uint32_t wI = lane; wI < 2 * a.words; wI += 32) bits[wI] = 0;
@@ -502,6 +511,18 @@ __global__ void __launch_bounds__(kAstarWarps * 32) k6_astar_search(SearchArgs a
                 } else
                 for (uint32_t base = 0; base < total; base += 32) {
                     const uint32_t idx = base + lane;
+                    // Pull the slots' lower ancestors into L1 now, in parallel with the edge-list loads: on a heap of 10^5
+                    // entries per search (GBs over all searches in flight) they are cold, and the replay below touches them
+                    // one child after the other — without this every moving child pays its own DRAM round trip.
+                    // (The addresses depend on hs only; levels above the 6th are shared by the whole batch.)
+                    {
+                        const uint32_t slot1 = hs + (uint32_t)lane + 1u;
+#pragma unroll
+                        for (int j = 1; j <= 6; j++) {
+                            const uint32_t q = slot1 >> j;
+                            if (q >= 1) touchL1(H + q - 1);
+                        }
+                    }
                     bool valid = false, hidden = false;
                     double f = 0.0;
                     uint32_t next = 0;
@@ -561,6 +582,7 @@ __global__ void __launch_bounds__(kAstarWarps * 32) k6_astar_search(SearchArgs a
             r.path_len = (uint8_t)pathLen;
             r.status = (uint8_t)status;
             r.pad = 0;
+            r.kcycles = (uint32_t)((clock64() - tStart) >> 10);
             a.results[qi] = r;
         }
         for (uint32_t wI = lane; wI < a.words; wI += 32) a.expandedBits[(size_t)qi * a.words + wI] = rbits[wI];

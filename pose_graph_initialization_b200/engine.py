@@ -92,14 +92,14 @@ ADJ_ENTRY_DTYPE = np.dtype([("vertex", np.uint32), ("index", np.uint32), ("next"
                             ("score", np.float64)], align=True)
 QUERY_DTYPE = np.dtype([("src", np.uint32), ("dst", np.uint32), ("cutoff", np.uint32), ("budget", np.uint32)], align=True)
 SEARCH_RESULT_DTYPE = np.dtype([("touched", np.uint32), ("pushes", np.uint32), ("path", np.uint16, (8,)), ("found", np.uint8),
-                                ("path_len", np.uint8), ("status", np.uint8), ("pad", np.uint8), ("reserved", np.uint32)],
+                                ("path_len", np.uint8), ("status", np.uint8), ("pad", np.uint8), ("kcycles", np.uint32)],
                                align=True)
 assert ADJ_ENTRY_DTYPE.itemsize == 24 and QUERY_DTYPE.itemsize == 16 and SEARCH_RESULT_DTYPE.itemsize == 32
 
 
 class PgiSearchStats(C.Structure):
     _fields_ = [("ms_search", C.c_double)] + [(k, C.c_uint64) for k in ("launches", "queries", "pops", "pushes", "overflows",
-                                                                         "h2d_bytes", "d2h_bytes")]
+                                                                         "h2d_bytes", "d2h_bytes", "kcycles_sum", "kcycles_longest")]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
