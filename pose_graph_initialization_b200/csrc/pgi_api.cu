@@ -106,7 +106,7 @@ struct pgi_ctx {
     pgi_search_result *h_results = nullptr;
     uint32_t *h_expBits = nullptr;
     uint32_t hApplyCap = 0, hQueryCap = 0;
-    int popLookahead = 1, stagedPush = 0;  // staged expansion measured equal to slightly slower on cfg2/cfg3: off by default
+    int popLookahead = 1, stagedPush = 1;
     cudaEvent_t evS0 = nullptr, evS1 = nullptr;
     pgi_search_stats sstats;
 };

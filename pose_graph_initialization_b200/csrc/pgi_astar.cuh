@@ -255,25 +255,79 @@ __device__ inline void popHeapWarp(HeapItemDev *H, uint32_t hs, int lane)
     siftUpWarp(H, h, shflItem(value, 0), lane);
 }
 
-// ---- staged expansion -------------------------------------------------------------------------------------------
-// The sift-ups of an expansion are a chain of dependent heap accesses, and on the heap in HBM every link of the chain
-// is an L2 round trip.  So an expansion is replayed in shared memory, kChunk edge-list entries at a time:
-//   * the chunk's admissible children are appended to a staging buffer (slots hs .. hs + C - 1 of the heap);
-//   * the slots a sequential std::push_heap of those children can touch within kConeLevels levels — for level j the
-//     contiguous window ((hs+1) >> j) - 1 .. ((hs+kChunk) >> j) - 1 — are loaded next to them in ONE parallel round trip
-//     (the addresses depend on hs only, so the loads are issued together with the edge-list loads);
-//   * children not larger than their parent stay where they are (see the header); the others are replayed in list order
-//     by one lane on the staged copy (shared-memory latency), continuing in global memory in the rare case a child
-//     climbs past the staged levels;
-//   * new slots and touched windows are written back in parallel.
-// Heaps of up to kStageItems - kChunk slots are staged whole (every child replayed: parents may be new slots).
-constexpr int kChunk = 128;
-constexpr int kConeLevels = 6;
-constexpr int kStageItems = 416;  // >= kChunk + sum_j (kChunk/2^j + 2) = 266
-__device__ __forceinline__ int coneOff(int j)  // staging index of level j's window (j = 1..kConeLevels)
+// ---- one batch of 32 edge-list entries, replayed directly on the heap in HBM ---------------------------------------------
+// Returns false if the heap slab is full.  `hidden` reports that the batch met an entry predicted by a later wave position
+// (everything behind it is hidden too).
+__device__ __forceinline__ bool pushBatchGlobal(const SearchArgs &a, HeapItemDev *H, uint32_t &hs, uint32_t &pushes,
+                                                const AdjDev *list, uint32_t total, uint32_t nc, uint32_t cutoff,
+                                                const uint32_t *bits, const double *simTo, double c0, double c1, uint32_t ni,
+                                                uint32_t base, int lane, bool &hiddenOut)
 {
-    // window sizes kChunk/2^j + 2 (66, 34, 18, 10, 6, 4): kChunk + sum_{k<j} (kChunk >> k) + 2 (j - 1)
-    return 2 * kChunk - (kChunk >> (j - 1)) + 2 * (j - 1);
+    const uint32_t ltMask = (1u << lane) - 1u;
+    const uint32_t idx = base + lane;
+    bool valid = false, hidden = false;
+    double f = 0.0;
+    uint32_t next = 0;
+    if (idx < total) {
+        const AdjDev e = list[idx];
+        if (idx >= nc && e.tag > cutoff)
+            hidden = true;  // predicted by a later wave position: not part of this search's graph
+        else if (!(e.score < 0.0)) {  // kMinimumInlierRatio is `const bool` receiving 0.0 (:613, :839)
+            next = e.next;
+            if (!((bits[next >> 5] >> (next & 31)) & 1u)) {  // nodeStates.find(next) == end  :855-856
+                const double edgeCost = c0 > e.score ? e.score : c0;  // MIN :843
+                const double h = simTo[next];
+                const double ntd = c1 < h ? h : c1;  // MAX :847
+                f = a.weight * edgeCost + a.oneMinusWeight * ntd;  // :851-852
+                valid = true;
+            }
+        }
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, valid);
+    hiddenOut = __ballot_sync(0xffffffffu, hidden) != 0;
+    const uint32_t cntv = __popc(m);
+    if (cntv) {
+        if (hs + cntv > a.heapCap) return false;
+        const uint32_t pos = hs + __popc(m & ltMask);
+        HeapItemDev it;
+        it.f = f; it.parent = ni; it.en = (idx << 16) | next;
+        if (valid) stItem(H + pos, it);
+        __syncwarp();
+        bool flag = false;
+        if (valid) flag = hs < 32u ? true : (ldItem(H + ((pos - 1) >> 1)).f < f);
+        uint32_t fm = __ballot_sync(0xffffffffu, flag);
+        while (fm) {
+            const int l = __ffs((int)fm) - 1;
+            fm &= fm - 1;
+            siftUpWarp(H, __shfl_sync(0xffffffffu, pos, l), shflItem(it, l), lane);
+            __syncwarp();
+        }
+        hs += cntv;
+        pushes += cntv;
+    }
+    return true;
+}
+
+// ---- staged expansion -------------------------------------------------------------------------------------------
+// A search of the benchmark scenes keeps 10^4..10^5 entries in its heap — GBs over the searches in flight, far beyond L2 —
+// and every std::push_heap that moves touches the slot's ancestors, one child after the other: on the heap in HBM each
+// moving child costs a memory round trip of its own (measured: 27 % of the kernel's stall samples on that one load, ~700
+// cycles per child).  So an expansion is replayed in shared memory, kChunk edge-list entries at a time:
+//   * the chunk's admissible children are appended to a staging buffer (slots hs .. hs + C - 1 of the heap);
+//   * ALL ancestors of those slots — for level j the contiguous window ((hs+1) >> j) - 1 .. ((hs+kChunk) >> j) - 1, up to
+//     the root — are loaded next to them in ONE parallel round trip (the addresses depend on hs only);
+//   * children not larger than their parent stay where they are (see the header); the others are replayed in list order
+//     on the staged copy with the warp-cooperative sift-up (lane j reads the j-th ancestor, ballot, shift), at
+//     shared-memory latency;
+//   * new slots and the touched windows are written back in parallel.
+// Chunks whose slots straddle two tree levels (the windows of different levels would then alias) or whose parents are
+// new slots themselves (heaps below kChunk entries) take the batch path above; both are rare.
+constexpr int kChunk = 128;
+constexpr int kStageItems = 320;  // kChunk + (66 + 34 + 18 + 10 + 6 + 4) + 3 per level from the 7th on (heaps < 2^21 slots)
+__device__ __forceinline__ int coneOff(int j)  // staging index of level j's window (level 0 = the new slots at index 0)
+{
+    // window sizes kChunk/2^j + 2 for j <= 6 (66, 34, 18, 10, 6, 4), 3 above
+    return j <= 6 ? 2 * kChunk - (kChunk >> (j - 1)) + 2 * (j - 1) : 266 + 3 * (j - 7);
 }
 __device__ __forceinline__ uint32_t coneStart(uint32_t hs, int j) { return ((hs + 1) >> j) - 1; }  // level-j ancestor of slot hs
 
@@ -283,7 +337,17 @@ __device__ inline bool expandStaged(const SearchArgs &a, HeapItemDev *H, uint32_
 {
     const uint32_t ltMask = (1u << lane) - 1u;
     for (uint32_t base = 0; base < total; base += kChunk) {
-        // ---- loads: 4 list entries per lane + the staging windows (all independent of each other)
+        const int depth = 31 - __clz((int)(hs + 1));  // ancestors of slot hs (root = level `depth`)
+        const bool stageable = hs >= (uint32_t)kChunk && depth == 31 - __clz((int)(hs + kChunk));
+        if (!stageable) {
+            bool hidden = false;
+            for (uint32_t b0 = base; b0 < total && b0 < base + kChunk && !hidden; b0 += 32)
+                if (!pushBatchGlobal(a, H, hs, pushes, list, total, nc, cutoff, bits, simTo, c0, c1, ni, b0, lane, hidden)) return false;
+            __syncwarp();
+            if (hidden) break;
+            continue;
+        }
+        // ---- loads: 4 list entries per lane + every ancestor window (all independent of each other)
         AdjDev e[4];
 #pragma unroll
         for (int b = 0; b < 4; b++) {
@@ -291,16 +355,10 @@ __device__ inline bool expandStaged(const SearchArgs &a, HeapItemDev *H, uint32_
             if (idx < total) e[b] = list[idx];
             else { e[b].score = 0.0; e[b].next = 0; e[b].tag = 0; }
         }
-        const bool small = hs + kChunk <= (uint32_t)kStageItems;
-        if (small) {
-            for (uint32_t p = lane; p < hs; p += 32) stItem(sStage + p, ldItem(H + p));
-        } else {
-#pragma unroll
-            for (int j = 1; j <= kConeLevels; j++) {
-                const uint32_t count = ((hs + kChunk) >> j) - ((hs + 1) >> j) + 1;
-                const int off = coneOff(j);
-                for (uint32_t k = lane; k < count; k += 32) stItem(sStage + off + k, ldItem(H + coneStart(hs, j) + k));
-            }
+        for (int j = 1; j <= depth; j++) {
+            const uint32_t count = ((hs + kChunk) >> j) - ((hs + 1) >> j) + 1;
+            const int off = coneOff(j);
+            for (uint32_t k = lane; k < count; k += 32) stItem(sStage + off + k, ldItem(H + coneStart(hs, j) + k));
         }
         // ---- evaluate the children (graph_traversal.h:830-862)
         bool valid[4];
@@ -343,13 +401,12 @@ __device__ inline bool expandStaged(const SearchArgs &a, HeapItemDev *H, uint32_
                     acc += __popc(m[b]);
                 }
             }
-            const uint32_t newBase = small ? hs : 0u;  // staging index of heap slot hs
 #pragma unroll
             for (int b = 0; b < 4; b++)
                 if (valid[b]) {
                     HeapItemDev it;
                     it.f = f[b]; it.parent = ni; it.en = ((base + 32u * b + lane) << 16) | next[b];
-                    stItem(sStage + newBase + cIdx[b], it);
+                    stItem(sStage + cIdx[b], it);
                 }
             __syncwarp();
             // ---- which children move at all (ordered list of their indices)
@@ -358,64 +415,41 @@ __device__ inline bool expandStaged(const SearchArgs &a, HeapItemDev *H, uint32_
             for (int b = 0; b < 4; b++) {
                 bool flag = false;
                 if (valid[b]) {
-                    if (small)
-                        flag = true;
-                    else {
-                        const uint32_t pp = (hs + cIdx[b] - 1) >> 1;
-                        flag = ldItem(sStage + coneOff(1) + (pp - coneStart(hs, 1))).f < f[b];
-                    }
+                    const uint32_t pp = (hs + cIdx[b] - 1) >> 1;
+                    flag = ldItem(sStage + coneOff(1) + (pp - coneStart(hs, 1))).f < f[b];
                 }
                 const uint32_t bal = __ballot_sync(0xffffffffu, flag);
                 if (flag) sList[nf + __popc(bal & ltMask)] = (uint16_t)cIdx[b];
                 nf += __popc(bal);
             }
             __syncwarp();
-            // ---- replay std::push_heap for those children, in list order, on the staged copy
-            int maxLev = 0;
-            if (lane == 0) {
-                if (small) {
-                    for (uint32_t i = 0; i < nf; i++) {
-                        const uint32_t p0 = hs + sList[i];
-                        const HeapItemDev item = ldItem(sStage + p0);
-                        siftUp(sStage, p0, item);
-                    }
-                } else {
-                    for (uint32_t i = 0; i < nf; i++) {
-                        const uint32_t c = sList[i];
-                        const HeapItemDev item = ldItem(sStage + c);
-                        uint32_t p = hs + c;          // heap position of the hole
-                        HeapItemDev *holeAt = sStage + c;  // where the hole lives (staging buffer or the heap itself)
-                        int lev = 0;
-                        while (p > 0) {
-                            const uint32_t pp = (p - 1) >> 1;
-                            HeapItemDev *parAt = lev < kConeLevels ? sStage + coneOff(lev + 1) + (pp - coneStart(hs, lev + 1)) : H + pp;
-                            const HeapItemDev par = ldItem(parAt);
-                            if (!(par.f < item.f)) break;
-                            stItem(holeAt, par);
-                            holeAt = parAt;
-                            p = pp;
-                            ++lev;
-                        }
-                        stItem(holeAt, item);
-                        const int touched = lev < kConeLevels ? lev : kConeLevels;
-                        maxLev = maxLev < touched ? touched : maxLev;
-                    }
+            // ---- replay std::push_heap for those children, in list order, on the staged copy (siftUpWarp on shared memory)
+            uint32_t maxLev = 0;
+            for (uint32_t i = 0; i < nf; i++) {
+                const uint32_t c = sList[i];
+                const uint32_t p1 = hs + c + 1;  // 1-based slot
+                const HeapItemDev value = ldItem(sStage + c);
+                const bool have = lane >= 1 && lane <= depth;
+                HeapItemDev anc;
+                anc.f = 0.0; anc.parent = 0; anc.en = 0;
+                if (have) anc = ldItem(sStage + coneOff(lane) + ((p1 >> lane) - 1 - coneStart(hs, lane)));
+                const uint32_t smaller = __ballot_sync(0xffffffffu, have && anc.f < value.f);
+                const uint32_t L = (uint32_t)__ffs((int)~(smaller >> 1)) - 1u;  // the ancestors below `value` are the first L
+                if (have && (uint32_t)lane <= L) {
+                    HeapItemDev *dst = lane == 1 ? sStage + c
+                                                 : sStage + coneOff(lane - 1) + ((p1 >> (lane - 1)) - 1 - coneStart(hs, lane - 1));
+                    stItem(dst, anc);
                 }
+                if (lane == 0 && L > 0) stItem(sStage + coneOff((int)L) + ((p1 >> L) - 1 - coneStart(hs, (int)L)), value);
+                maxLev = maxLev < L ? L : maxLev;
+                __syncwarp();
             }
-            maxLev = __shfl_sync(0xffffffffu, maxLev, 0);
-            __syncwarp();
             // ---- write back
-            if (small) {
-                for (uint32_t p = lane; p < hs + C; p += 32) stItem(H + p, ldItem(sStage + p));
-            } else {
-                for (uint32_t c = lane; c < C; c += 32) stItem(H + hs + c, ldItem(sStage + c));
-#pragma unroll
-                for (int j = 1; j <= kConeLevels; j++)
-                    if (j <= maxLev) {
-                        const uint32_t count = ((hs + kChunk) >> j) - ((hs + 1) >> j) + 1;
-                        const int off = coneOff(j);
-                        for (uint32_t k = lane; k < count; k += 32) stItem(H + coneStart(hs, j) + k, ldItem(sStage + off + k));
-                    }
+            for (uint32_t c = lane; c < C; c += 32) stItem(H + hs + c, ldItem(sStage + c));
+            for (int j = 1; j <= (int)maxLev; j++) {
+                const uint32_t count = ((hs + kChunk) >> j) - ((hs + 1) >> j) + 1;
+                const int off = coneOff(j);
+                for (uint32_t k = lane; k < count; k += 32) stItem(H + coneStart(hs, j) + k, ldItem(sStage + off + k));
             }
             hs += C;
             pushes += C;
@@ -439,7 +473,6 @@ __global__ void __launch_bounds__(kAstarWarps * 32) k6_astar_search(SearchArgs a
     const uint32_t slot = blockIdx.x * kAstarWarps + warp;
     HeapItemDev *H = a.heaps + (size_t)slot * a.heapCap;
     ArenaNodeDev *A = a.arenas + (size_t)slot * a.arenaCap;
-    const uint32_t ltMask = (1u << lane) - 1u;
     for (;;) {
         uint32_t qi = 0;
         if (lane == 0) qi = atomicAdd(a.nextQuery, 1u);
@@ -508,62 +541,12 @@ __global__ void __launch_bounds__(kAstarWarps * 32) k6_astar_search(SearchArgs a
                 bool overflow = false;
                 if (a.staged) {
                     overflow = !expandStaged(a, H, hs, pushes, list, total, nc, cutoff, bits, simTo, c0, c1, ni, sStage, sList, lane);
-                } else
-                for (uint32_t base = 0; base < total; base += 32) {
-                    const uint32_t idx = base + lane;
-                    // Pull the slots' lower ancestors into L1 now, in parallel with the edge-list loads: on a heap of 10^5
-                    // entries per search (GBs over all searches in flight) they are cold, and the replay below touches them
-                    // one child after the other — without this every moving child pays its own DRAM round trip.
-                    // (The addresses depend on hs only; levels above the 6th are shared by the whole batch.)
-                    {
-                        const uint32_t slot1 = hs + (uint32_t)lane + 1u;
-#pragma unroll
-                        for (int j = 1; j <= 6; j++) {
-                            const uint32_t q = slot1 >> j;
-                            if (q >= 1) touchL1(H + q - 1);
-                        }
+                } else {
+                    for (uint32_t base = 0; base < total; base += 32) {
+                        bool hidden = false;
+                        if (!pushBatchGlobal(a, H, hs, pushes, list, total, nc, cutoff, bits, simTo, c0, c1, ni, base, lane, hidden)) { overflow = true; break; }
+                        if (hidden) break;  // predicted entries are in position order: everything behind is hidden too
                     }
-                    bool valid = false, hidden = false;
-                    double f = 0.0;
-                    uint32_t next = 0;
-                    if (idx < total) {
-                        const AdjDev e = list[idx];
-                        if (idx >= nc && e.tag > cutoff)
-                            hidden = true;  // predicted by a later wave position: not part of this search's graph
-                        else if (!(e.score < 0.0)) {  // kMinimumInlierRatio is `const bool` receiving 0.0 (:613, :839)
-                            next = e.next;
-                            if (!((bits[next >> 5] >> (next & 31)) & 1u)) {  // nodeStates.find(next) == end  :855-856
-                                const double edgeCost = c0 > e.score ? e.score : c0;
-                                const double h = simTo[next];
-                                const double ntd = c1 < h ? h : c1;
-                                f = a.weight * edgeCost + a.oneMinusWeight * ntd;  // :851-852
-                                valid = true;
-                            }
-                        }
-                    }
-                    const uint32_t m = __ballot_sync(0xffffffffu, valid);
-                    const uint32_t anyHidden = __ballot_sync(0xffffffffu, hidden);
-                    const uint32_t cntv = __popc(m);
-                    if (cntv) {
-                        if (hs + cntv > a.heapCap) { overflow = true; break; }
-                        const uint32_t pos = hs + __popc(m & ltMask);
-                        HeapItemDev it;
-                        it.f = f; it.parent = ni; it.en = (idx << 16) | next;
-                        if (valid) stItem(H + pos, it);
-                        __syncwarp();
-                        bool flag = false;
-                        if (valid) flag = hs < 32u ? true : (ldItem(H + ((pos - 1) >> 1)).f < f);
-                        uint32_t fm = __ballot_sync(0xffffffffu, flag);
-                        while (fm) {
-                            const int l = __ffs((int)fm) - 1;
-                            fm &= fm - 1;
-                            siftUpWarp(H, __shfl_sync(0xffffffffu, pos, l), shflItem(it, l), lane);
-                            __syncwarp();
-                        }
-                        hs += cntv;
-                        pushes += cntv;
-                    }
-                    if (anyHidden) break;  // predicted entries are in position order: everything behind is hidden too
                 }
                 if (overflow) { status = SEARCH_HEAP_OVERFLOW; break; }
                 if (budget && pushes > budget) { status = SEARCH_BUDGET; break; }
