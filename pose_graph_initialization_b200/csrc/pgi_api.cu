@@ -64,6 +64,8 @@ struct pgi_ctx {
     uint32_t k4aSmem = 0;  // PGI_K4A_SMEM: dynamic shared memory per K4a CTA, an occupancy throttle (L2 footprint of the 5 KB stacks)
     uint32_t k4bCtas = 2;  // K4b CTAs per SM (PGI_K4B_CTAS): fewer lanes = more polynomials per lane = better refill balance
     bool k4Split = true;   // PGI_K4_SPLIT=0 selects the one-kernel k4_fallback_solve
+    bool k1Tma = true;     // PGI_K1_TMA=0: always the direct-load K1
+    uint32_t numSms = 148;
     uint32_t *d_k3Scratch = nullptr;  // per wave slot: K3 vote totals + arrival ticket (zero between launches)
     uint64_t *d_maskOffset = nullptr;
     pgi_verdict *d_verdicts = nullptr;
@@ -361,7 +363,14 @@ pgi_status submitWave(pgi_ctx *ctx, const Registration &r, uint32_t n, const uin
     a.k3Scratch = ctx->d_k3Scratch; a.dkList = ctx->d_dkList; a.dkCtl = ctx->d_dkCtl;
 
     CK(cudaEventRecord(ctx->evStart, s));  // kernel-only timing: the wave's small H2D copies are before this event
-    k1_score_hypotheses<<<n, kCtaThreads, 0, s>>>(a);
+    // full waves stream the correspondences through shared memory with bulk async copies (persistent CTAs, one per SM);
+    // small waves and waves that want byte masks take the one-CTA-per-pair kernel
+    if (ctx->k1Tma && n >= 2u * ctx->numSms && !(flags & PGI_WAVE_MASKS)) {
+        const int k1Smem = kK1Stages * kK1TileRows * 32;
+        CK(cudaFuncSetAttribute(k1_score_hypotheses_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, k1Smem));
+        k1_score_hypotheses_tma<<<std::min<uint32_t>(n, ctx->numSms), kCtaThreads, k1Smem, s>>>(a);
+    } else
+        k1_score_hypotheses<<<n, kCtaThreads, 0, s>>>(a);
     CK(cudaEventRecord(ctx->evK1, s));
     ctx->stats.launches += 1;
     ctx->fbLaunched = false;
@@ -392,7 +401,7 @@ pgi_status submitWave(pgi_ctx *ctx, const Registration &r, uint32_t n, const uin
                 if (ctx->k4Split) {
                     CK(cudaMemsetAsync(ctx->d_dkCtl, 0, 8, s));
                     k4a_polynomial<<<(threads + 127) / 128, 128, ctx->k4aSmem, s>>>(a, c);
-                    k4b_roots<<<std::min<uint32_t>((threads + 127) / 128, 148u * ctx->k4bCtas), 128, 0, s>>>(a);
+                    k4b_roots<<<std::min<uint32_t>((threads + 127) / 128, ctx->numSms * ctx->k4bCtas), 128, 0, s>>>(a);
                     k4c_solutions<<<(threads + 127) / 128, 128, 0, s>>>(a, c);
                     ctx->stats.launches += 2;
                 } else
@@ -479,6 +488,8 @@ pgi_status pgi_create(const pgi_config *cfg, pgi_ctx **out)
     pgi_ctx *ctx = new pgi_ctx();
     ctx->cfg = *cfg;
     if (const char *e = getenv("PGI_K4_SPLIT")) ctx->k4Split = atoi(e) != 0;
+    if (const char *e = getenv("PGI_K1_TMA")) ctx->k1Tma = atoi(e) != 0;
+    ctx->numSms = (uint32_t)std::max(1, prop.multiProcessorCount);
     if (const char *e = getenv("PGI_K4A_SMEM")) ctx->k4aSmem = (uint32_t)std::max(0, std::min(200 * 1024, atoi(e)));
     if (const char *e = getenv("PGI_K4B_CTAS")) ctx->k4bCtas = (uint32_t)std::max(1, std::min(4, atoi(e)));
     if (ctx->cfg.min_inliers == 0) ctx->cfg.min_inliers = 20;
