@@ -287,8 +287,8 @@ def main():
     ap.add_argument("--cv2-yardstick", default="", help=argparse.SUPPRESS)
     ap.add_argument("--workers", type=int, default=1, help=argparse.SUPPRESS)
     ap.add_argument("--lazy", action="store_true", help="run the fallback lazily inside the waves instead of prefetching it")
-    ap.add_argument("--host-search", action="store_true", help="A* on the host thread pool instead of the device (K6)")
-    ap.add_argument("--search-min-batch", type=int, default=16, help="rounds with fewer searches stay on the host pool")
+    ap.add_argument("--device-search", action="store_true", help="A* rounds on the device (K6) beside the host thread pool (default: host pool only)")
+    ap.add_argument("--search-min-batch", type=int, default=64, help="device search: rounds with fewer searches stay on the host pool")
     ap.add_argument("--verify", type=int, default=-1, help="after the timed steps, check the last run against the CPU oracle: "
                     "N evenly spaced tuples (0 = every pair) + sequential host replay; exit code 3 on any mismatch")
     ap.add_argument("--verify-replay", type=int, default=-1, help="queue positions replayed by the oracle host (-1 = whole queue up to 400 views, else 20000; 0 = whole queue)")
@@ -325,7 +325,7 @@ def main():
 
     scene = make_scene(args.config)  # same seed on every rank => identical scene
     if args.wave <= 0:
-        args.wave = B.default_wave_size(len(scene["focal"]), world, not args.host_search)
+        args.wave = B.default_wave_size(len(scene["focal"]), world, args.device_search)
     # the step's host inputs live in PINNED memory (every step copies them host->device)
     for key in ("matches", "kp", "sim", "pair_views", "m_offset", "kp_offset", "focal", "size"):
         src = np.ascontiguousarray(scene[key])
@@ -337,7 +337,7 @@ def main():
     pgb = B.PoseGraphBuilder(kCoreNumber_=max(1, (os.cpu_count() or 1) // world),  # ranks share the box's cores
                              kSimilarityThreshold_=0.0, scene=scene, device=local_rank, wave_size=args.wave,
                              prefetch_fallback=not args.lazy, overlap_fallback=not args.no_overlap, research_window=args.window,
-                             fallback_wave=args.fb_wave, prefetch_streams=args.fb_streams, gpu_search=not args.host_search,
+                             fallback_wave=args.fb_wave, prefetch_streams=args.fb_streams, gpu_search=args.device_search,
                              gpu_search_min_batch=args.search_min_batch, group=group, rank=rank, world_size=world)
     pgb.prepare()
     fp64_peak = pgb.engine.fp64_peak(fused=False)
@@ -476,7 +476,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_resident / K, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {**config_keys(args.config, scene), "wave": args.wave, "fallback": "lazy" if args.lazy else "prefetched",
-                       "search": "host pool" if args.host_search else "device (K6), rounds below %d searches on the host pool" % args.search_min_batch,
+                       "search": "host pool" if not args.device_search else "device (K6) + host pool, rounds below %d searches on the host pool alone" % args.search_min_batch,
                        "l2": "inputs (%.1f GB of FP64 correspondences) larger than the 126 MB L2" % (P * n_corr * 32 / 1e9),
                        "parallelism": "pairs sharded over %d rank(s), verdict exchange per wave round" % world},
             "timing": "e2e: K x (prepare + run) back to back; value: the K run() regions (inputs resident), each bracketed by "

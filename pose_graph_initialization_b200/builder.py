@@ -318,10 +318,10 @@ class RecordExchanger:
         return self.np_out[:n].copy().view(RECORD_DTYPE)
 
 
-def default_wave_size(n_views, world_size=1, gpu_search=True):
-    """Queue positions per speculative wave.  Host-pool searches: 256 on one GPU (fewest re-searches), 512 with several
-    ranks (every round of a wave costs a record exchange).  Device searches (K6) are cheap in bulk and a round costs
-    a kernel round trip, so waves are larger (measured on cfg2/cfg3, scripts/gpu_r2_b.sh)."""
+def default_wave_size(n_views, world_size=1, gpu_search=False):
+    """Queue positions per speculative wave.  Host-pool searches: 256 on one GPU (fewest re-searches: measured optimum on
+    cfg2 and cfg3), 512 with several ranks (every round of a wave costs a record exchange).  Device searches (K6) need
+    large rounds to fill the GPU: 2048 (at the price of ~1.6x the searches)."""
     if not gpu_search:
         return 256 if world_size == 1 else 512
     return 1024 if n_views < 600 else 2048
@@ -356,7 +356,7 @@ class PoseGraphBuilder:
                  kImagePath_="", kWorkspacePath_="", kSimilarityGraphPath_="", kFocalLengthPath_="",
                  kUsePathFinding_=True, kUseGPU_=True, kUseEpipolarHashing_=False, *, scene=None, device=0,
                  wave_size=None, prefetch_fallback=True, fallback_wave=1024, overlap_fallback=True, research_window=0,
-                 prefetch_streams=2, native_loop=True, gpu_search=True, gpu_search_min_batch=16,
+                 prefetch_streams=2, native_loop=True, gpu_search=False, gpu_search_min_batch=64,
                  group=None, rank=0, world_size=1):
         if not kUseGPU_:
             raise ValueError("the B200 path has no CPU implementation (kUseGPU_ must be true)")
@@ -397,7 +397,10 @@ class PoseGraphBuilder:
         # one rank: the wave loop itself runs in C++ (pgb_run_wave calling pgi_submit_wave / pgi_wait_wave directly);
         # several ranks: the Python loop below, because the record exchange goes through torch.distributed
         self.native_loop = bool(native_loop)
-        # speculative A* searches of a wave round as one batched device call (K6) instead of the host thread pool
+        # gpu_search=True: the speculative A* searches of a wave round run as one batched device call (K6) beside the host
+        # thread pool.  Exact, but measured no faster than the pool alone on the benchmark scenes: a
+        # round lasts as long as its longest search and a search is a chain of dependent heap operations, so it is off by
+        # default.
         self.gpu_search = bool(gpu_search) and os.environ.get("PGI_GPU_SEARCH", "1") != "0"
         self.gpu_search_min_batch = int(gpu_search_min_batch)
         self.prefetch_streams = int(prefetch_streams)

@@ -213,6 +213,8 @@ struct AStarScratch {
     std::vector<uint32_t> mark;  // per-vertex stamp of "expanded in this search"
     uint32_t epoch = 0;
     std::vector<uint32_t> path;
+    std::vector<double> childF;   // scratch of one expansion: combined cost / list entry of the admissible children
+    std::vector<uint32_t> childE;
 };
 
 // Predicted edges of the open wave, layered over the committed graph.
@@ -395,15 +397,37 @@ void aStar(const GraphView &gv, const double *sim /*transposed*/, uint32_t V, ui
             const size_t hs0 = hs;
             const double wgt = weight;
             uint32_t entry = 0;
-            auto push = [&](const Adj &e, uint32_t ent) __attribute__((always_inline)) {
-                if (e.score < 0.0) return;  // kMinimumInlierRatio is `const bool` receiving 0.0 (:613, :839)
+            // Two passes over the edge list.  Pass 1 evaluates every entry without a data-dependent branch (admissible
+            // children are compacted into a scratch array by a predicated store); pass 2 replays std::push_heap for them
+            // in list order.  Same operations on the same operands as the one-pass loop, but the sift-up's unpredictable
+            // exit no longer sits between two gathers.
+            const size_t listLen = rl.size() + (ol ? ol->size() : 0);
+            if (S.childF.size() < listLen) { S.childF.resize(listLen); S.childE.resize(listLen); }
+            double *cf = S.childF.data();
+            uint32_t *ce = S.childE.data();
+            size_t cnt = 0;
+            auto eval = [&](const Adj &e, uint32_t ent) __attribute__((always_inline)) {
                 uint32_t next = e.next;     // (v == dst) ? src : dst  :838-840
                 if (lv != v) next = e.next == v ? lv : e.next;  // stale list of another vertex (unreachable, see above)
-                if (mark[next] == epoch) return;  // nodeStates.find(next) != end  :855-856
+                // kMinimumInlierRatio is `const bool` receiving 0.0 (:613, :839); nodeStates.find(next) != end  :855-856
+                const bool ok = !(e.score < 0.0) && mark[next] != epoch;
                 const double edgeCost = c0 > e.score ? e.score : c0;  // MIN :843
                 const double h = simTo[next];  // std::clamp(getSimilarity(next, to), 0, 1)  :594 (pre-clamped table)
                 const double nextToDest = c1 < h ? h : c1;  // MAX :847
-                const double combined = wgt * edgeCost + oneMinusWeight * nextToDest;  // :851-852
+                cf[cnt] = wgt * edgeCost + oneMinusWeight * nextToDest;  // :851-852
+                ce[cnt] = ent;
+                cnt += ok ? 1 : 0;
+            };
+            const Adj *ra = rl.data();
+            const uint32_t nr = (uint32_t)rl.size();
+            for (; entry < nr; ++entry) eval(ra[entry], entry);
+            if (ol)
+                for (const OvAdj &oe : *ol) {
+                    if (oe.pos >= gv.cutoff) break;
+                    eval(oe.a, entry++);
+                }
+            for (size_t i = 0; i < cnt; i++) {
+                const double combined = cf[i];
                 size_t hole = hs++;
                 while (hole > 0) {
                     const size_t parent = (hole - 1) / 2;
@@ -411,16 +435,8 @@ void aStar(const GraphView &gv, const double *sim /*transposed*/, uint32_t V, ui
                     first[hole] = first[parent];
                     hole = parent;
                 }
-                first[hole] = HeapItem{combined, ni, ent};
-            };
-            const Adj *ra = rl.data();
-            const uint32_t nr = (uint32_t)rl.size();
-            for (; entry < nr; ++entry) push(ra[entry], entry);
-            if (ol)
-                for (const OvAdj &oe : *ol) {
-                    if (oe.pos >= gv.cutoff) break;
-                    push(oe.a, entry++);
-                }
+                first[hole] = HeapItem{combined, ni, ce[i]};
+            }
             out.pushes += (uint32_t)(hs - hs0);
         }
     }
@@ -715,11 +731,16 @@ void searchPosition(pgb_builder *b, uint32_t k, AStarScratch &S)
     it.searched = true;
 }
 
-void searchOnHost(pgb_builder *b, const std::vector<uint32_t> &todo)
+void searchOnHost(pgb_builder *b, const std::vector<uint32_t> &todoIn)
 {
-    if (b->cfg.host_threads <= 1 || todo.size() < 4) {
-        for (uint32_t k : todo) searchPosition(b, k, b->scratch[0]);
+    if (b->cfg.host_threads <= 1 || todoIn.size() < 4) {
+        for (uint32_t k : todoIn) searchPosition(b, k, b->scratch[0]);
     } else {
+        // search costs are heavy-tailed (the longest search of a round is ~10x the mean): hand the threads the
+        // longest-looking searches first (a position's previous search is the estimate), so that no thread starts a
+        // long one when the others are about to run dry
+        std::vector<uint32_t> todo(todoIn);
+        std::stable_sort(todo.begin(), todo.end(), [&](uint32_t x, uint32_t y) { return b->wave[x].pushes > b->wave[y].pushes; });
         std::atomic<size_t> next(0);
         b->pool.run([&](int tid) {
             for (;;) {

@@ -368,7 +368,7 @@ pgi_status submitWave(pgi_ctx *ctx, const Registration &r, uint32_t n, const uin
     if (ctx->k1Tma && n >= 2u * ctx->numSms && !(flags & PGI_WAVE_MASKS)) {
         const int k1Smem = kK1Stages * kK1TileRows * 32;
         CK(cudaFuncSetAttribute(k1_score_hypotheses_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, k1Smem));
-        k1_score_hypotheses_tma<<<std::min<uint32_t>(n, ctx->numSms), kCtaThreads, k1Smem, s>>>(a);
+        k1_score_hypotheses_tma<<<std::min<uint32_t>(n, ctx->numSms), kK1TmaThreads, k1Smem, s>>>(a);
     } else
         k1_score_hypotheses<<<n, kCtaThreads, 0, s>>>(a);
     CK(cudaEventRecord(ctx->evK1, s));

@@ -265,6 +265,8 @@ __global__ void __launch_bounds__(kCtaThreads, 3) k1_score_hypotheses(WaveArgs a
 // ---------------------------------------------------------------------------------------------
 constexpr int kK1Stages = 4;
 constexpr int kK1TileRows = 1024;  // 32 KB per stage
+constexpr int kK1TmaThreads = 1024; // one row of the tile per thread: 32 warps keep the FP64 pipe fed (scoring a row is ~45 non-fused
+                                    // FP64 operations: at the HBM rate of 32 B per row that is about half the FP64 issue rate)
 
 __device__ __forceinline__ uint32_t smemAddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbarInit(uint64_t *bar, uint32_t count)
@@ -321,12 +323,12 @@ __device__ __forceinline__ bool k1Next(const WaveArgs &a, K1Cursor &c)
     return k1Load(a, c);
 }
 
-__global__ void __launch_bounds__(kCtaThreads, 1) k1_score_hypotheses_tma(WaveArgs a)
+__global__ void __launch_bounds__(kK1TmaThreads, 1) k1_score_hypotheses_tma(WaveArgs a)
 {
     extern __shared__ __align__(128) unsigned char k1Smem[];
     double4 *tiles = reinterpret_cast<double4 *>(k1Smem);
     __shared__ __align__(8) uint64_t sFull[kK1Stages];
-    __shared__ uint32_t sCnt[2][kCtaThreads / 32];
+    __shared__ uint32_t sCnt[2][kK1TmaThreads / 32];
     __shared__ uint32_t sDecision, sValidSel;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
@@ -389,9 +391,9 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k1_score_hypotheses_tma(WaveAr
             const double4 *tile = tiles + (size_t)st * kK1TileRows;
             uint32_t *bits = a.bits + ((size_t)w * 2 + (1u - sValidSel)) * a.bitsStride;
 #pragma unroll
-            for (int u = 0; u < kK1TileRows / kCtaThreads; u++) {
-                const uint32_t li = u * kCtaThreads + threadIdx.x;  // row within the tile
-                if (u * kCtaThreads >= rows) break;                  // warp-uniform
+            for (int u = 0; u < kK1TileRows / kK1TmaThreads; u++) {
+                const uint32_t li = u * kK1TmaThreads + threadIdx.x;  // row within the tile
+                if (u * kK1TmaThreads >= rows) break;                  // warp-uniform
                 bool t = false, in = false;
                 if (li < rows) {
                     const double4 c = tile[li];
@@ -434,7 +436,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k1_score_hypotheses_tma(WaveAr
             __syncthreads();
             if (threadIdx.x == 0) {
                 uint32_t t = 0, in = 0;
-                for (int k = 0; k < kCtaThreads / 32; k++) { t += sCnt[0][k]; in += sCnt[1][k]; }
+                for (int k = 0; k < kK1TmaThreads / 32; k++) { t += sCnt[0][k]; in += sCnt[1][k]; }
                 const bool passed = noTest || (t >= a.testMinInliers);    // GT:221
                 testCount = t < a.testMinInliers ? t : a.testMinInliers;  // early exit leaves inlierNumber_ at the minimum
                 if (passed) {
