@@ -205,6 +205,21 @@ pgi_status pgi_graph_search(pgi_ctx *ctx, uint32_t n, const pgi_query *queries, 
                             pgi_search_result *results, uint32_t *expanded_bits);
 pgi_status pgi_graph_stats(pgi_ctx *ctx, pgi_search_stats *out, int32_t reset);
 
+/* ---- epipolar-hashing guided matcher (K7) ----------------------------------------------------------------
+ * HashingBasedMatcherWithPose<false, 45>::match (matcher.h:199-405), the matcher PoseGraphBuilder::guidedMatching runs
+ * on an accepted pair (pose_graph_builder.h:717-783): keypoints of the destination image are hashed by the angle of
+ * their epipolar line, every source keypoint searches its bin for the descriptor nearest neighbour among the points
+ * within 0.75 px symmetric epipolar distance, count-corrected Lowe ratio.  kp_*: n x 2 float pixels (cv::KeyPoint.pt),
+ * desc_*: n x dim float; pose_q_t: T_dst_src; K_*: 3x3 row-major intrinsics; size_*: width, height.
+ * matches_out (capacity n_src x 2: source index, destination index, in source order) and ratios_out (capacity n_src)
+ * receive match()'s output, *n_out their number.  The top-`maximum_points` selection of guidedMatching is host work on
+ * that list (pose_graph_builder.h:760-782).  prepared_or_null: 14 doubles (F, epipole, min angle, range, bins). */
+pgi_status pgi_guided_match(pgi_ctx *ctx, uint32_t n_src, const float *kp_src, const float *desc_src, uint32_t n_dst,
+                            const float *kp_dst, const float *desc_dst, uint32_t dim, const double *pose_q_t,
+                            const double *K_src, const double *K_dst, const int32_t *size_src, const int32_t *size_dst,
+                            int32_t bin_number, uint32_t *matches_out, double *ratios_out, uint32_t *n_out,
+                            double *prepared_or_null);
+
 pgi_status pgi_get_stats(pgi_ctx *ctx, pgi_stats *out);
 pgi_status pgi_reset_stats(pgi_ctx *ctx);
 

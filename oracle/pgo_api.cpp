@@ -14,6 +14,7 @@
 #include "pgo_fallback.hpp"
 #include "pgo_geom.hpp"
 #include "pgo_host.hpp"
+#include "pgo_matcher.hpp"
 
 using namespace pgo;
 
@@ -243,6 +244,39 @@ int pgo_scene_pipeline_batch(uint64_t V, const double *focal, const double *size
     worker();
     for (auto &th : pool) th.join();
     return used;
+}
+
+// ---- epipolar-hashing guided matcher (matcher.h:199-405, pose_graph_builder.h:717-783) -----------------------
+// prep_out[16] = F[9], epipole[2], minAngle, angularRange, binNumber.  Returns the number of matches of match();
+// sel_* receive guidedMatching's selection (at most max_points entries), *n_sel its size.
+uint64_t pgo_guided_match(const float *kpS, uint64_t nS, const float *dS, const float *kpD, uint64_t nD, const float *dD,
+                          int dim, const double *poseQt, const double *Ks, const double *Kd, int wS, int hS, int wD, int hD,
+                          int binNumber, uint64_t maxPoints, uint32_t *matches, double *ratios, uint64_t cap,
+                          uint32_t *selMatches, double *selRatios, uint64_t *nSel, double *prepOut)
+{
+    double E[9];
+    essentialFromPose(se3FromArray(poseQt), E);
+    const matcher::Prepared P = matcher::prepare(E, Ks, Kd, wS, hS, wD, hD, binNumber);
+    if (prepOut) {
+        for (int k = 0; k < 9; k++) prepOut[k] = P.F[k];
+        prepOut[9] = P.epipole[0]; prepOut[10] = P.epipole[1]; prepOut[11] = P.minAngle; prepOut[12] = P.angularRange;
+        prepOut[13] = P.binNumber;
+    }
+    std::vector<std::pair<uint32_t, uint32_t>> m;
+    std::vector<double> r;
+    matcher::match(kpS, nS, dS, kpD, nD, dD, dim, P, m, r);
+    for (size_t i = 0; i < m.size() && i < cap; i++) {
+        matches[2 * i] = m[i].first; matches[2 * i + 1] = m[i].second; ratios[i] = r[i];
+    }
+    if (nSel) {
+        std::vector<std::tuple<uint32_t, uint32_t, double>> sel;
+        matcher::selectMatches(m, r, maxPoints, sel);
+        *nSel = sel.size();
+        for (size_t i = 0; i < sel.size(); i++) {
+            selMatches[2 * i] = std::get<0>(sel[i]); selMatches[2 * i + 1] = std::get<1>(sel[i]); selRatios[i] = std::get<2>(sel[i]);
+        }
+    }
+    return m.size();
 }
 
 // ---- host loop -----------------------------------------------------------------------------------

@@ -365,3 +365,25 @@ def replay_scene(scene, log, sim_threshold=0.0, min_points=50, max_depth=5, weig
                        _p(out, _i64p))
     keys = ["checked", "mismatches", "edges", "searches", "first_bad", "first_bad_field"]
     return dict(zip(keys, (int(x) for x in out)))
+
+
+def guided_match(kp_src, desc_src, kp_dst, desc_dst, pose_qt, K_src, K_dst, size_src, size_dst, bin_number=45, max_points=100):
+    """HashingBasedMatcherWithPose<false, 45>::match + guidedMatching's selection.  Returns dict(matches[n,2], ratios[n],
+    selected[(src, dst, ratio)], prepared[14])."""
+    L = lib()
+    ks = np.ascontiguousarray(kp_src, dtype=np.float32); kd = np.ascontiguousarray(kp_dst, dtype=np.float32)
+    ds = np.ascontiguousarray(desc_src, dtype=np.float32); dd = np.ascontiguousarray(desc_dst, dtype=np.float32)
+    cap = len(ks)
+    m = np.zeros((max(cap, 1), 2), dtype=np.uint32); r = np.zeros(max(cap, 1))
+    sm = np.zeros((max(cap, 1), 2), dtype=np.uint32); sr = np.zeros(max(cap, 1))
+    nsel = C.c_uint64(0)
+    prep = np.zeros(16)
+    L.pgo_guided_match.restype = C.c_uint64
+    n = L.pgo_guided_match(_p(ks, _fp), C.c_uint64(len(ks)), _p(ds, _fp), _p(kd, _fp), C.c_uint64(len(kd)), _p(dd, _fp),
+                           C.c_int(ds.shape[1]), _p(_d(pose_qt), _dp), _p(_d(K_src), _dp), _p(_d(K_dst), _dp),
+                           C.c_int(int(size_src[0])), C.c_int(int(size_src[1])), C.c_int(int(size_dst[0])), C.c_int(int(size_dst[1])),
+                           C.c_int(bin_number), C.c_uint64(max_points), _p(m, _u32p), _p(r, _dp), C.c_uint64(cap),
+                           _p(sm, _u32p), _p(sr, _dp), C.byref(nsel), _p(prep, _dp))
+    n = int(n)
+    k = int(nsel.value)
+    return dict(matches=m[:n].copy(), ratios=r[:n].copy(), selected_matches=sm[:k].copy(), selected_ratios=sr[:k].copy(), prepared=prep[:14].copy())

@@ -15,6 +15,7 @@
 #include "../../include/pgi.h"
 #include "pgi_kernels.cuh"
 #include "pgi_astar.cuh"
+#include "pgi_matcher.cuh"
 
 using namespace pgi;
 
@@ -929,6 +930,80 @@ pgi_status pgi_graph_stats(pgi_ctx *ctx, pgi_search_stats *out, int32_t reset)
     if (!ctx) return PGI_ERR_INVALID;
     if (out) *out = ctx->sstats;
     if (reset) memset(&ctx->sstats, 0, sizeof ctx->sstats);
+    return PGI_OK;
+}
+
+pgi_status pgi_guided_match(pgi_ctx *ctx, uint32_t n_src, const float *kp_src, const float *desc_src, uint32_t n_dst,
+                            const float *kp_dst, const float *desc_dst, uint32_t dim, const double *pose_q_t,
+                            const double *K_src, const double *K_dst, const int32_t *size_src, const int32_t *size_dst,
+                            int32_t bin_number, uint32_t *matches_out, double *ratios_out, uint32_t *n_out,
+                            double *prepared_or_null)
+{
+    if (!ctx) return PGI_ERR_INVALID;
+    if (!pose_q_t || !K_src || !K_dst || !size_src || !size_dst || !n_out || (n_src && (!kp_src || !desc_src || !matches_out || !ratios_out)) ||
+        (n_dst && (!kp_dst || !desc_dst)) || dim == 0 || bin_number > kMatchMaxBins) {
+        ctx->err = "bad argument";
+        return PGI_ERR_INVALID;
+    }
+    CK(cudaSetDevice(ctx->cfg.device));
+    *n_out = 0;
+    if (n_src == 0 || n_dst == 0) return PGI_OK;
+    cudaStream_t s = ctx->stream;
+    const size_t bS = (size_t)n_src, bD = (size_t)n_dst;
+    // one scratch allocation per call: this entry point is the reference-shaped single-pair call
+    unsigned char *d = nullptr;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t oKpS = 0, oDS = oKpS + al(bS * 8), oKpD = oDS + al(bS * dim * 4), oDD = oKpD + al(bD * 8), oBin = oDD + al(bD * dim * 4),
+                 oList = oBin + al(bD), oCand = oList + al(bD * 4), oRatio = oCand + al(bS * 4), oM = oRatio + al(bS * 8),
+                 oR = oM + al(bS * 8), oN = oR + al(bS * 8), oPrep = oN + 256, total = oPrep + 256;
+    CK(cudaMalloc((void **)&d, total));
+    auto fail = [&](cudaError_t e) { cudaFree(d); ctx->err = cudaGetErrorString(e); return PGI_ERR_CUDA; };
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(d + oKpS, kp_src, bS * 8, cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(e);
+    if ((e = cudaMemcpyAsync(d + oDS, desc_src, bS * dim * 4, cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(e);
+    if ((e = cudaMemcpyAsync(d + oKpD, kp_dst, bD * 8, cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(e);
+    if ((e = cudaMemcpyAsync(d + oDD, desc_dst, bD * dim * 4, cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(e);
+    MatchArgs a;
+    a.kpS = reinterpret_cast<const float2 *>(d + oKpS); a.dS = reinterpret_cast<const float *>(d + oDS);
+    a.kpD = reinterpret_cast<const float2 *>(d + oKpD); a.dD = reinterpret_cast<const float *>(d + oDD);
+    a.nS = n_src; a.nD = n_dst; a.dim = dim;
+    {
+        double E[9];
+        // E = [t]x R of the pose (pose.h:46-55), as the matcher reads it from Pose::getEssentialMatrix (matcher.h:218)
+        double R[9];
+        const double *q = pose_q_t;
+        const double tx = 2.0 * q[0], ty = 2.0 * q[1], tz = 2.0 * q[2];
+        const double twx = tx * q[3], twy = ty * q[3], twz = tz * q[3], txx = tx * q[0], txy = ty * q[0], txz = tz * q[0];
+        const double tyy = ty * q[1], tyz = tz * q[1], tzz = tz * q[2];
+        R[0] = 1.0 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+        R[3] = txy + twz; R[4] = 1.0 - (txx + tzz); R[5] = tyz - twx;
+        R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1.0 - (txx + tyy);
+        const double Cx[9] = {0.0, -q[6], q[5], q[6], 0.0, -q[4], -q[5], q[4], 0.0};
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) E[i * 3 + j] = Cx[i * 3 + 0] * R[j] + (Cx[i * 3 + 1] * R[3 + j] + Cx[i * 3 + 2] * R[6 + j]);
+        for (int k = 0; k < 9; k++) { a.E[k] = E[k]; a.Ks[k] = K_src[k]; a.Kd[k] = K_dst[k]; }
+    }
+    a.wS = size_src[0]; a.hS = size_src[1]; a.wD = size_dst[0]; a.hD = size_dst[1]; a.binNumber = bin_number;
+    a.binOfD = d + oBin; a.binList = reinterpret_cast<uint32_t *>(d + oList); a.cand = reinterpret_cast<uint32_t *>(d + oCand);
+    a.candRatio = reinterpret_cast<double *>(d + oRatio); a.matches = reinterpret_cast<uint32_t *>(d + oM);
+    a.ratios = reinterpret_cast<double *>(d + oR); a.nOut = reinterpret_cast<uint32_t *>(d + oN);
+    a.prepOut = reinterpret_cast<double *>(d + oPrep);
+    k7_guided_match<<<1, kMatchThreads, 0, s>>>(a);
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail(e);
+    uint32_t n = 0;
+    if ((e = cudaMemcpyAsync(&n, d + oN, 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return fail(e);
+    if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return fail(e);
+    if (n > n_src) n = n_src;
+    if (n) {
+        if ((e = cudaMemcpy(matches_out, d + oM, (size_t)n * 8, cudaMemcpyDeviceToHost)) != cudaSuccess) return fail(e);
+        if ((e = cudaMemcpy(ratios_out, d + oR, (size_t)n * 8, cudaMemcpyDeviceToHost)) != cudaSuccess) return fail(e);
+    }
+    if (prepared_or_null && (e = cudaMemcpy(prepared_or_null, d + oPrep, 14 * 8, cudaMemcpyDeviceToHost)) != cudaSuccess) return fail(e);
+    cudaFree(d);
+    *n_out = n;
+    ctx->stats.launches += 1;
+    ctx->stats.h2d_bytes += bS * (8 + dim * 4) + bD * (8 + dim * 4);
+    ctx->stats.d2h_bytes += (size_t)n * 16 + 4;
     return PGI_OK;
 }
 

@@ -46,7 +46,7 @@ EXPORTS = [
     "pgi_version", "pgi_device_count", "pgi_create", "pgi_destroy", "pgi_last_error", "pgi_register_pairs",
     "pgi_register_scene", "pgi_share_pairs", "pgi_read_pair", "pgi_submit_wave", "pgi_wait_wave", "pgi_wait_wave_device",
     "pgi_estimate_pose", "pgi_test_pose", "pgi_graph_init", "pgi_graph_apply", "pgi_graph_search", "pgi_graph_stats",
-    "pgi_get_stats", "pgi_reset_stats", "pgi_dbg_sampson",
+    "pgi_guided_match", "pgi_get_stats", "pgi_reset_stats", "pgi_dbg_sampson",
     "pgi_dbg_five_point", "pgi_dbg_pose_from_essential", "pgi_dbg_fp64_peak",
 ]
 
@@ -254,6 +254,37 @@ class Engine:
         s = PgiSearchStats()
         self._ck(self.lib.pgi_graph_stats(self.h, C.byref(s), C.c_int32(1 if reset else 0)))
         return s.as_dict()
+
+    # ---- epipolar-hashing guided matcher (K7) ---------------------------------------------------------------
+    def guided_match(self, kp_src, desc_src, kp_dst, desc_dst, pose_qt, K_src, K_dst, size_src, size_dst, bin_number=45,
+                     max_points=100):
+        """HashingBasedMatcherWithPose<false, 45>::match on the device + guidedMatching's selection
+        (pose_graph_builder.h:717-783).  Returns dict(matches[n,2], ratios[n], selected[(src, dst, value)], prepared[14])."""
+        ks = np.ascontiguousarray(kp_src, dtype=np.float32).reshape(-1, 2)
+        kd = np.ascontiguousarray(kp_dst, dtype=np.float32).reshape(-1, 2)
+        ds = np.ascontiguousarray(desc_src, dtype=np.float32)
+        dd = np.ascontiguousarray(desc_dst, dtype=np.float32)
+        if ds.ndim != 2 or dd.ndim != 2 or len(ds) != len(ks) or len(dd) != len(kd) or ds.shape[1] != dd.shape[1]:
+            raise ValueError("descriptors must be [n_src, dim] / [n_dst, dim] arrays matching the keypoints")
+        m = np.zeros((max(len(ks), 1), 2), dtype=np.uint32)
+        r = np.zeros(max(len(ks), 1))
+        n = C.c_uint32(0)
+        prep = np.zeros(14)
+        ss = np.asarray(size_src, dtype=np.int32)
+        sd = np.asarray(size_dst, dtype=np.int32)
+        self._ck(self.lib.pgi_guided_match(self.h, C.c_uint32(len(ks)), _ptr(ks), _ptr(ds), C.c_uint32(len(kd)), _ptr(kd), _ptr(dd),
+                                           C.c_uint32(ds.shape[1]), _ptr(_f64(pose_qt)), _ptr(_f64(K_src)), _ptr(_f64(K_dst)),
+                                           _ptr(ss), _ptr(sd), C.c_int32(bin_number), _ptr(m), _ptr(r), C.byref(n), _ptr(prep)))
+        k = int(n.value)
+        matches, ratios = m[:k].copy(), r[:k].copy()
+        # guidedMatching's selection (pose_graph_builder.h:760-782): the max_points smallest values (min-heap order on
+        # (value, index)); at most max_points matches: every match carries descriptorDistances[0]
+        if k > max_points:
+            order = np.lexsort((np.arange(k), ratios))[:max_points]
+            selected = [(int(matches[i, 0]), int(matches[i, 1]), float(ratios[i])) for i in order]
+        else:
+            selected = [(int(a), int(b), float(ratios[0])) for a, b in matches]
+        return dict(matches=matches, ratios=ratios, selected=selected, prepared=prep)
 
     # ---- stats / debug -------------------------------------------------------------------------------------
     def stats(self):
