@@ -41,6 +41,11 @@
 
 #include "../../include/pgb.h"
 
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#define PGB_HAVE_AVX2_PATH 1
+#endif
+
 namespace {
 
 // ---- pose algebra (Sophus/Eigen semantics; scalar evaluation order as documented in DESIGN.md) --------
@@ -185,6 +190,10 @@ struct Visibility {
     }
 };
 
+// PGB_EXPAND selects the expansion loop of the host A* (identical results; for measurements): 0 one pass, 1 two passes,
+// 2 (default) two passes with the AVX2 evaluation and batched sift-up flags
+static const int kExpandVariant = getenv("PGB_EXPAND") ? atoi(getenv("PGB_EXPAND")) : 2;
+
 struct AStarOut {
     bool found = false;
     SE3 pose = se3Identity();
@@ -214,7 +223,7 @@ struct AStarScratch {
     uint32_t epoch = 0;
     std::vector<uint32_t> path;
     std::vector<double> childF;   // scratch of one expansion: combined cost / list entry of the admissible children
-    std::vector<uint32_t> childE;
+    std::vector<uint32_t> childE, childMove;
 };
 
 // Predicted edges of the open wave, layered over the committed graph.
@@ -300,6 +309,48 @@ bool recoverPath(const GraphView &gv, const PathT *path, size_t n, SE3 &pose)
     }
     return true;
 }
+
+// Pass 1 of an expansion over the committed entries, four at a time with AVX2 (runtime-dispatched; the scalar loop below
+// is the definition).  Same IEEE operations per entry — compare + select for MIN/MAX (graph_traversal.h:843-848), two
+// multiplications and one addition, never fused — so the costs are bit-identical to the scalar loop's.
+#ifdef PGB_HAVE_AVX2_PATH
+static const bool kUseAvx2 = __builtin_cpu_supports("avx2") && !(getenv("PGB_NO_AVX2") && atoi(getenv("PGB_NO_AVX2")) != 0);
+__attribute__((target("avx2"))) size_t evalEntriesAvx2(const Adj *ra, uint32_t n, const uint32_t *mark, uint32_t epoch,
+                                                       const double *simTo, double c0, double c1, double wgt, double omw,
+                                                       double *cf, uint32_t *ce, size_t cnt, uint32_t &entryOut)
+{
+    const __m256d vc0 = _mm256_set1_pd(c0), vc1 = _mm256_set1_pd(c1), vw = _mm256_set1_pd(wgt), vo = _mm256_set1_pd(omw);
+    const __m256d zero = _mm256_setzero_pd();
+    const __m128i vep = _mm_set1_epi32((int)epoch);
+    uint32_t e = 0;
+    for (; e + 4 <= n; e += 4) {
+        // Adj = {u32 next, u32 edge, f64 score}: two 32-byte loads hold entries (e, e+1) and (e+2, e+3)
+        const __m256d a0 = _mm256_loadu_pd(reinterpret_cast<const double *>(ra + e));
+        const __m256d a1 = _mm256_loadu_pd(reinterpret_cast<const double *>(ra + e + 2));
+        const __m256d sc = _mm256_permute4x64_pd(_mm256_unpackhi_pd(a0, a1), 0xD8);  // scores of e, e+1, e+2, e+3
+        const __m256i hd = _mm256_castpd_si256(_mm256_permute4x64_pd(_mm256_unpacklo_pd(a0, a1), 0xD8));  // (next, edge) x 4
+        const __m128i nx = _mm256_castsi256_si128(_mm256_permutevar8x32_epi32(hd, _mm256_setr_epi32(0, 2, 4, 6, 0, 0, 0, 0)));
+        const __m128i mk = _mm_i32gather_epi32(reinterpret_cast<const int *>(mark), nx, 4);
+        const __m256d h = _mm256_i32gather_pd(simTo, nx, 8);
+        const __m256d ec = _mm256_blendv_pd(vc0, sc, _mm256_cmp_pd(vc0, sc, _CMP_GT_OQ));  // c0 > score ? score : c0
+        const __m256d nd = _mm256_blendv_pd(vc1, h, _mm256_cmp_pd(vc1, h, _CMP_LT_OQ));    // c1 < h ? h : c1
+        const __m256d f = _mm256_add_pd(_mm256_mul_pd(vw, ec), _mm256_mul_pd(vo, nd));
+        const int neg = _mm256_movemask_pd(_mm256_cmp_pd(sc, zero, _CMP_LT_OQ));           // score < 0
+        const int seen = _mm_movemask_ps(_mm_castsi128_ps(_mm_cmpeq_epi32(mk, vep)));      // mark[next] == epoch
+        const int ok = ~(neg | seen) & 15;
+        alignas(32) double fo[4];
+        _mm256_store_pd(fo, f);
+#pragma GCC unroll 4
+        for (int k = 0; k < 4; k++) {
+            cf[cnt] = fo[k];
+            ce[cnt] = e + (uint32_t)k;
+            cnt += (ok >> k) & 1;
+        }
+    }
+    entryOut = e;
+    return cnt;
+}
+#endif
 
 // AStarTraversal<ImageSimilarityHeuristics>::getPath with the arguments of pose_graph_builder.h:834-841.
 void aStar(const GraphView &gv, const double *sim /*transposed*/, uint32_t V, uint32_t from, uint32_t to, size_t maxDepth,
@@ -420,23 +471,82 @@ void aStar(const GraphView &gv, const double *sim /*transposed*/, uint32_t V, ui
             };
             const Adj *ra = rl.data();
             const uint32_t nr = (uint32_t)rl.size();
+            if (kExpandVariant == 0) {
+                // the one-pass form (kept for A/B measurements, PGB_EXPAND=0): evaluate and push entry by entry
+                auto push1 = [&](const Adj &e, uint32_t ent) __attribute__((always_inline)) {
+                    if (e.score < 0.0) return;
+                    uint32_t next = e.next;
+                    if (lv != v) next = e.next == v ? lv : e.next;
+                    if (mark[next] == epoch) return;
+                    const double edgeCost = c0 > e.score ? e.score : c0;
+                    const double h = simTo[next];
+                    const double nextToDest = c1 < h ? h : c1;
+                    const double combined = wgt * edgeCost + oneMinusWeight * nextToDest;
+                    size_t hole = hs++;
+                    while (hole > 0) {
+                        const size_t parent = (hole - 1) / 2;
+                        if (!(first[parent].f < combined)) break;
+                        first[hole] = first[parent];
+                        hole = parent;
+                    }
+                    first[hole] = HeapItem{combined, ni, ent};
+                };
+                for (; entry < nr; ++entry) push1(ra[entry], entry);
+                if (ol)
+                    for (const OvAdj &oe : *ol) {
+                        if (oe.pos >= gv.cutoff) break;
+                        push1(oe.a, entry++);
+                    }
+                out.pushes += (uint32_t)(hs - hs0);
+                continue;
+            }
+#ifdef PGB_HAVE_AVX2_PATH
+            if (kExpandVariant >= 2 && kUseAvx2 && lv == v) cnt = evalEntriesAvx2(ra, nr, mark, epoch, simTo, c0, c1, wgt, oneMinusWeight, cf, ce, cnt, entry);
+#endif
             for (; entry < nr; ++entry) eval(ra[entry], entry);
             if (ol)
                 for (const OvAdj &oe : *ol) {
                     if (oe.pos >= gv.cutoff) break;
                     eval(oe.a, entry++);
                 }
-            for (size_t i = 0; i < cnt; i++) {
-                const double combined = cf[i];
-                size_t hole = hs++;
-                while (hole > 0) {
-                    const size_t parent = (hole - 1) / 2;
-                    if (!(first[parent].f < combined)) break;
-                    first[hole] = first[parent];
-                    hole = parent;
+            // Pass 2.  A sequential std::push_heap of child i touches only ancestors of its slot; ancestors that were in the
+            // heap before this expansion can only grow while its children are pushed, so a child that is not larger than
+            // its parent NOW stays where it is appended.  All children are appended first, the ones that move are then
+            // replayed in list order (when the heap is smaller than the batch, parents may be new slots: replay them all).
+            if (kExpandVariant >= 2 && hs >= cnt) {
+                size_t nMove = 0;
+                uint32_t *mv = S.childMove.size() < cnt ? (S.childMove.resize(listLen), S.childMove.data()) : S.childMove.data();
+                for (size_t i = 0; i < cnt; i++) {
+                    const size_t slot = hs + i;
+                    first[slot] = HeapItem{cf[i], ni, ce[i]};
+                    mv[nMove] = (uint32_t)i;
+                    nMove += first[(slot - 1) / 2].f < cf[i] ? 1 : 0;  // slot >= 1 here (hs >= cnt >= 1)
                 }
-                first[hole] = HeapItem{combined, ni, ce[i]};
-            }
+                for (size_t k = 0; k < nMove; k++) {
+                    const size_t i = mv[k];
+                    const double combined = cf[i];
+                    size_t hole = hs + i;
+                    while (hole > 0) {
+                        const size_t parent = (hole - 1) / 2;
+                        if (!(first[parent].f < combined)) break;
+                        first[hole] = first[parent];
+                        hole = parent;
+                    }
+                    first[hole] = HeapItem{combined, ni, ce[i]};
+                }
+                hs += cnt;
+            } else
+                for (size_t i = 0; i < cnt; i++) {
+                    const double combined = cf[i];
+                    size_t hole = hs++;
+                    while (hole > 0) {
+                        const size_t parent = (hole - 1) / 2;
+                        if (!(first[parent].f < combined)) break;
+                        first[hole] = first[parent];
+                        hole = parent;
+                    }
+                    first[hole] = HeapItem{combined, ni, ce[i]};
+                }
             out.pushes += (uint32_t)(hs - hs0);
         }
     }

@@ -367,7 +367,7 @@ pgi_status submitWave(pgi_ctx *ctx, const Registration &r, uint32_t n, const uin
     // full waves stream the correspondences through shared memory with bulk async copies (persistent CTAs, one per SM);
     // small waves and waves that want byte masks take the one-CTA-per-pair kernel
     if (ctx->k1Tma && n >= 2u * ctx->numSms && !(flags & PGI_WAVE_MASKS)) {
-        const int k1Smem = kK1Stages * kK1TileRows * 32;
+        const int k1Smem = kK1Stages * kK1TileRows * 32 + (int)sizeof(K1Meta);
         CK(cudaFuncSetAttribute(k1_score_hypotheses_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, k1Smem));
         k1_score_hypotheses_tma<<<std::min<uint32_t>(n, ctx->numSms), kK1TmaThreads, k1Smem, s>>>(a);
     } else

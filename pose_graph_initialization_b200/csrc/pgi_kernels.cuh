@@ -296,176 +296,202 @@ __device__ __forceinline__ void bulkLoad(void *dstSmem, const void *srcGlobal, u
                  : "memory");
 }
 
-struct K1Cursor {  // walks the (slot, hypothesis, tile) work items of one CTA in order
-    uint32_t w, h, h1, row0, N;
-    uint64_t r0;
+// Work of one CTA: the wave slots blockIdx.x, blockIdx.x + gridDim.x, ...  Their descriptors (row range, hypothesis
+// range, threshold, E of the first hypothesis) are fetched kK1MetaSlots at a time by as many threads in parallel and kept
+// in shared memory, so the streaming loop below never waits on a chain of dependent global loads (pair id -> offsets ->
+// threshold / hypothesis) between two tiles.
+constexpr int kK1MetaSlots = 256;
+struct K1Meta {
+    uint64_t r0[kK1MetaSlots];
+    double thr[kK1MetaSlots];
+    double E[kK1MetaSlots][9];
+    uint32_t N[kK1MetaSlots], h0[kK1MetaSlots], h1[kK1MetaSlots], table[kK1MetaSlots];
 };
-__device__ __forceinline__ bool k1Load(const WaveArgs &a, K1Cursor &c)  // position on slot c.w; false if past the wave
+struct K1Cursor {  // walks the (slot, hypothesis, tile) items of the descriptors in shared memory
+    uint32_t k, h, row0;
+};
+__device__ __forceinline__ bool k1Next(const K1Meta &m, uint32_t nSlots, K1Cursor &c)
 {
-    while (c.w < a.n) {
-        const uint32_t pid = a.pairId[c.w];
-        c.r0 = a.offset[pid];
-        c.N = (uint32_t)(a.offset[pid + 1] - c.r0);
-        c.h = a.hypOffset[c.w];
-        c.h1 = a.hypOffset[c.w + 1];
-        c.row0 = 0;
-        return true;
-    }
-    return false;
-}
-// advance to the next tile; returns false when the CTA's work is exhausted.  Slots without hypotheses or rows yield one
-// empty item so that their state is still written.
-__device__ __forceinline__ bool k1Next(const WaveArgs &a, K1Cursor &c)
-{
-    if (c.h < c.h1 && c.row0 + kK1TileRows < c.N) { c.row0 += kK1TileRows; return true; }
-    if (c.h + 1 < c.h1) { ++c.h; c.row0 = 0; return true; }
-    c.w += gridDim.x;
-    return k1Load(a, c);
+    if (c.h < m.h1[c.k] && c.row0 + kK1TileRows < m.N[c.k]) { c.row0 += kK1TileRows; return true; }
+    if (c.h + 1 < m.h1[c.k]) { ++c.h; c.row0 = 0; return true; }
+    if (++c.k >= nSlots) return false;
+    c.h = m.h0[c.k];
+    c.row0 = 0;
+    return true;
 }
 
 __global__ void __launch_bounds__(kK1TmaThreads, 1) k1_score_hypotheses_tma(WaveArgs a)
 {
     extern __shared__ __align__(128) unsigned char k1Smem[];
     double4 *tiles = reinterpret_cast<double4 *>(k1Smem);
+    K1Meta &meta = *reinterpret_cast<K1Meta *>(k1Smem + (size_t)kK1Stages * kK1TileRows * 32);
     __shared__ __align__(8) uint64_t sFull[kK1Stages];
     __shared__ uint32_t sCnt[2][kK1TmaThreads / 32];
-    __shared__ uint32_t sDecision, sValidSel;
+    __shared__ uint32_t sValidSel;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         for (int s = 0; s < kK1Stages; s++) mbarInit(&sFull[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        sValidSel = 0;
     }
     __syncthreads();
     const bool noTest = (a.flags & PGI_WAVE_NO_TEST) != 0;
+    uint32_t issued = 0, consumed = 0;  // items whose copy was started (thread 0) / that were scored (all threads)
 
-    K1Cursor prod, cons;
-    prod.w = cons.w = blockIdx.x;
-    bool prodLive = k1Load(a, prod), consLive = k1Load(a, cons);
-    uint32_t issued = 0, consumed = 0;
-    auto issue = [&]() {  // thread 0: arm the stage and start the copy of the producer cursor's tile
-        const uint32_t rows = prod.h < prod.h1 && prod.row0 < prod.N ? min((uint32_t)kK1TileRows, prod.N - prod.row0) : 0u;
-        const int st = issued % kK1Stages;
-        if (rows) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of the stage precede the async write
-            mbarExpectTx(&sFull[st], rows * 32u);
-            bulkLoad(tiles + (size_t)st * kK1TileRows, reinterpret_cast<const double4 *>(a.corr) + prod.r0 + prod.row0, rows * 32u, &sFull[st]);
-        } else
-            mbarExpectTx(&sFull[st], 0u);  // empty item: the phase still completes
-        ++issued;
-        prodLive = k1Next(a, prod);
-    };
-    if (threadIdx.x == 0)
-        for (int k = 0; k < kK1Stages - 1 && prodLive; k++) issue();
-
-    // per-slot bookkeeping (thread 0) and per-hypothesis partial counts (lane 0 of every warp)
-    uint32_t flags = 0, testCount = 0, pathInliers = 0, cTest = 0, cInl = 0;
-    double E[9];
-    double thrT = 0.0, thrTsq = 0.0;
-    bool slotStart = true, hypStart = true;
-    if (threadIdx.x == 0) sValidSel = 0;
-    __syncthreads();
-    while (consLive) {
-        const uint32_t w = cons.w, N = cons.N;
-        if (slotStart) {
+    for (uint32_t slotBase = 0; blockIdx.x + (uint64_t)slotBase * gridDim.x < a.n; slotBase += kK1MetaSlots) {
+        // ---- descriptors of the next kK1MetaSlots slots, one thread per slot
+        const uint32_t remaining = (uint32_t)((a.n - blockIdx.x - (uint64_t)slotBase * gridDim.x + gridDim.x - 1) / gridDim.x);
+        const uint32_t nSlots = remaining < (uint32_t)kK1MetaSlots ? remaining : (uint32_t)kK1MetaSlots;
+        if (threadIdx.x < nSlots) {
+            const uint32_t t = threadIdx.x, w = blockIdx.x + (slotBase + t) * gridDim.x;
             const uint32_t pid = a.pairId[w];
-            thrT = a.thrOverride > 0.0 ? a.thrOverride : a.thrMultiplier * a.thr[pid];  // 1.5 * thr_norm  (PGB:800, :964)
-            thrTsq = thrT * thrT;                                                       // GT:184
-            flags = testCount = pathInliers = 0;
-            slotStart = false;
-        }
-        const bool haveHyp = cons.h < cons.h1;
-        if (haveHyp && hypStart) {
-            double qt[7];
+            const uint64_t r0 = a.offset[pid];
+            meta.r0[t] = r0;
+            meta.N[t] = (uint32_t)(a.offset[pid + 1] - r0);
+            meta.h0[t] = a.hypOffset[w];
+            meta.h1[t] = a.hypOffset[w + 1];
+            meta.thr[t] = a.thrOverride > 0.0 ? a.thrOverride : a.thrMultiplier * a.thr[pid];  // 1.5 * thr_norm  (PGB:800, :964)
+            meta.table[t] = a.pairTable[pid];
+            if (meta.h1[t] > meta.h0[t]) {
+                double qt[7], E[9];
 #pragma unroll
-            for (int k = 0; k < 7; k++) qt[k] = a.hyp[7 * (size_t)cons.h + k];
-            essentialFromPose(qt, E);
-            cTest = cInl = 0;
-            hypStart = false;
-        }
-        if (threadIdx.x == 0 && prodLive) issue();  // refills the stage consumed in the previous iteration
-        const int st = consumed % kK1Stages;
-        mbarWait(&sFull[st], (consumed / kK1Stages) & 1u);
-        ++consumed;
-        const uint32_t rows = haveHyp && cons.row0 < N ? min((uint32_t)kK1TileRows, N - cons.row0) : 0u;
-        if (rows) {
-            const double4 *tile = tiles + (size_t)st * kK1TileRows;
-            uint32_t *bits = a.bits + ((size_t)w * 2 + (1u - sValidSel)) * a.bitsStride;
+                for (int k = 0; k < 7; k++) qt[k] = a.hyp[7 * (size_t)meta.h0[t] + k];
+                essentialFromPose(qt, E);
 #pragma unroll
-            for (int u = 0; u < kK1TileRows / kK1TmaThreads; u++) {
-                const uint32_t li = u * kK1TmaThreads + threadIdx.x;  // row within the tile
-                if (u * kK1TmaThreads >= rows) break;                  // warp-uniform
-                bool t = false, in = false;
-                if (li < rows) {
-                    const double4 c = tile[li];
-                    const double x1 = c.x, y1 = c.y, x2 = c.z, y2 = c.w;
-                    const double rxc = E[0] * x2 + E[3] * y2 + E[6];
-                    const double ryc = E[1] * x2 + E[4] * y2 + E[7];
-                    const double rwc = E[2] * x2 + E[5] * y2 + E[8];
-                    const double r = (x1 * rxc + y1 * ryc + rwc);
-                    const double rx = E[0] * x1 + E[1] * y1 + E[2];
-                    const double ry = E[3] * x1 + E[4] * y1 + E[5];
-                    const double r2 = r * r;
-                    const double den = rxc * rxc + ryc * ryc + rx * rx + ry * ry;
-                    const double q1 = thrTsq * den, q2 = thrT * den;
-                    const double lo = 1.0 - 8.8817841970012523e-16, hi = 1.0 + 8.8817841970012523e-16;  // 1 -+ 2^-50 (see k1_score_hypotheses)
-                    const bool sure1 = q1 > 1e-290 && (r2 < q1 * lo || r2 > q1 * hi);
-                    const bool sure2 = q2 > 1e-290 && (r2 < q2 * lo || r2 > q2 * hi);
-                    if (sure1 && sure2) {
-                        t = r2 < q1;
-                        in = r2 < q2;
-                    } else {
-                        const double sres = r2 / den;
-                        t = sres < thrTsq;  // GT:214
-                        in = sres < thrT;   // GT:164 (un-squared threshold, reproduced)
+                for (int k = 0; k < 9; k++) meta.E[t][k] = E[k];
+            }
+        }
+        __syncthreads();
+
+        K1Cursor prod{0, meta.h0[0], 0}, cons{0, meta.h0[0], 0};
+        bool prodLive = true, consLive = true;
+        auto issue = [&]() {  // thread 0: arm the stage and start the copy of the producer cursor's tile
+            const uint32_t N = meta.N[prod.k];
+            const uint32_t rows = prod.h < meta.h1[prod.k] && prod.row0 < N ? min((uint32_t)kK1TileRows, N - prod.row0) : 0u;
+            const int st = issued % kK1Stages;
+            if (rows) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of the stage precede the async write
+                mbarExpectTx(&sFull[st], rows * 32u);
+                bulkLoad(tiles + (size_t)st * kK1TileRows, reinterpret_cast<const double4 *>(a.corr) + meta.r0[prod.k] + prod.row0, rows * 32u,
+                         &sFull[st]);
+            } else
+                mbarExpectTx(&sFull[st], 0u);  // empty item (no hypothesis / no rows): the phase still completes
+            ++issued;
+            prodLive = k1Next(meta, nSlots, prod);
+        };
+        if (threadIdx.x == 0)
+            for (int k = 0; k < kK1Stages - 1 && prodLive; k++) issue();
+
+        uint32_t flags = 0, testCount = 0, pathInliers = 0, cTest = 0, cInl = 0;  // per slot (thread 0) / per hypothesis (lane 0)
+        double E[9];
+        double thrT = 0.0, thrTsq = 0.0;
+        bool slotStart = true, hypStart = true;
+        while (consLive) {
+            const uint32_t k = cons.k, N = meta.N[k];
+            const uint32_t w = blockIdx.x + (slotBase + k) * gridDim.x;
+            if (slotStart) {
+                thrT = meta.thr[k];
+                thrTsq = thrT * thrT;  // GT:184
+                flags = testCount = pathInliers = 0;
+                slotStart = false;
+            }
+            const bool haveHyp = cons.h < meta.h1[k];
+            if (haveHyp && hypStart) {
+                if (cons.h == meta.h0[k]) {
+#pragma unroll
+                    for (int q = 0; q < 9; q++) E[q] = meta.E[k][q];
+                } else {
+                    double qt[7];
+#pragma unroll
+                    for (int q = 0; q < 7; q++) qt[q] = a.hyp[7 * (size_t)cons.h + q];
+                    essentialFromPose(qt, E);
+                }
+                cTest = cInl = 0;
+                hypStart = false;
+            }
+            if (threadIdx.x == 0 && prodLive) issue();  // refills the stage consumed in the previous iteration
+            const int st = consumed % kK1Stages;
+            mbarWait(&sFull[st], (consumed / kK1Stages) & 1u);
+            ++consumed;
+            const uint32_t rows = haveHyp && cons.row0 < N ? min((uint32_t)kK1TileRows, N - cons.row0) : 0u;
+            if (rows) {
+                const double4 *tile = tiles + (size_t)st * kK1TileRows;
+                uint32_t *bits = a.bits + ((size_t)w * 2 + (1u - sValidSel)) * a.bitsStride;
+                const uint32_t li = threadIdx.x;  // one row of the tile per thread
+                if ((li & ~31u) < rows) {          // warp-uniform: the warp's 32-row group starts inside the tile
+                    bool t = false, in = false;
+                    if (li < rows) {
+                        const double4 c = tile[li];
+                        const double x1 = c.x, y1 = c.y, x2 = c.z, y2 = c.w;
+                        const double rxc = E[0] * x2 + E[3] * y2 + E[6];
+                        const double ryc = E[1] * x2 + E[4] * y2 + E[7];
+                        const double rwc = E[2] * x2 + E[5] * y2 + E[8];
+                        const double r = (x1 * rxc + y1 * ryc + rwc);
+                        const double rx = E[0] * x1 + E[1] * y1 + E[2];
+                        const double ry = E[3] * x1 + E[4] * y1 + E[5];
+                        const double r2 = r * r;
+                        const double den = rxc * rxc + ryc * ryc + rx * rx + ry * ry;
+                        const double q1 = thrTsq * den, q2 = thrT * den;
+                        const double lo = 1.0 - 8.8817841970012523e-16, hi = 1.0 + 8.8817841970012523e-16;  // 1 -+ 2^-50 (see k1_score_hypotheses)
+                        const bool sure1 = q1 > 1e-290 && (r2 < q1 * lo || r2 > q1 * hi);
+                        const bool sure2 = q2 > 1e-290 && (r2 < q2 * lo || r2 > q2 * hi);
+                        if (sure1 && sure2) {
+                            t = r2 < q1;
+                            in = r2 < q2;
+                        } else {
+                            const double sres = r2 / den;
+                            t = sres < thrTsq;  // GT:214
+                            in = sres < thrT;   // GT:164 (un-squared threshold, reproduced)
+                        }
+                    }
+                    const uint32_t bt = __ballot_sync(0xffffffffu, t);
+                    const uint32_t bi = __ballot_sync(0xffffffffu, in);
+                    if (lane == 0) {
+                        cTest += __popc(bt);
+                        cInl += __popc(bi);
+                        bits[(cons.row0 + li) >> 5] = bi;
                     }
                 }
-                const uint32_t bt = __ballot_sync(0xffffffffu, t);
-                const uint32_t bi = __ballot_sync(0xffffffffu, in);
-                if (lane == 0) {
-                    cTest += __popc(bt);
-                    cInl += __popc(bi);
-                    if (li < rows) bits[(cons.row0 + li) >> 5] = bi;
+            }
+            const bool hypEnd = haveHyp && cons.row0 + kK1TileRows >= N;
+            const bool slotEnd = !haveHyp || (hypEnd && cons.h + 1 >= meta.h1[k]);
+            if (hypEnd) {
+                if (lane == 0) { sCnt[0][warp] = cTest; sCnt[1][warp] = cInl; }
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    uint32_t t = 0, in = 0;
+                    for (int q = 0; q < kK1TmaThreads / 32; q++) { t += sCnt[0][q]; in += sCnt[1][q]; }
+                    const bool passed = noTest || (t >= a.testMinInliers);    // GT:221
+                    testCount = t < a.testMinInliers ? t : a.testMinInliers;  // early exit leaves inlierNumber_ at the minimum
+                    if (passed) {
+                        flags = ST_HAVE_HYP | ST_TEST_PASSED;
+                        pathInliers = in;
+                        sValidSel = 1u - sValidSel;  // the buffer just written becomes the sampler's input
+                    } else
+                        flags |= ST_HAVE_HYP;
+                    atomicAdd(a.counters + 0, (unsigned long long)N);
                 }
+                hypStart = true;
             }
-        }
-        // end of this hypothesis (its last tile, or an empty item)?
-        const bool hypEnd = haveHyp && cons.row0 + kK1TileRows >= N;
-        const bool slotEnd = !haveHyp || (hypEnd && cons.h + 1 >= cons.h1);
-        if (hypEnd) {
-            if (lane == 0) { sCnt[0][warp] = cTest; sCnt[1][warp] = cInl; }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                uint32_t t = 0, in = 0;
-                for (int k = 0; k < kK1TmaThreads / 32; k++) { t += sCnt[0][k]; in += sCnt[1][k]; }
-                const bool passed = noTest || (t >= a.testMinInliers);    // GT:221
-                testCount = t < a.testMinInliers ? t : a.testMinInliers;  // early exit leaves inlierNumber_ at the minimum
-                if (passed) {
-                    flags = ST_HAVE_HYP | ST_TEST_PASSED;
-                    pathInliers = in;
-                    sValidSel = 1u - sValidSel;  // the buffer just written becomes the sampler's input
-                } else
-                    flags |= ST_HAVE_HYP;
-                atomicAdd(a.counters + 0, (unsigned long long)N);
+            if (slotEnd && threadIdx.x == 0) {
+                SlotState &s = a.state[w];
+                s.testCount = testCount;
+                s.pathInliers = (flags & ST_TEST_PASSED) ? pathInliers : 0u;
+                s.inlierCount = 0;
+                s.tableIdx = meta.table[k];
+                s.pad = sValidSel;  // which bit buffer K2 samples from
+                s.models = 0;
+                s.it = 0;
+                uint32_t f = flags;
+                if ((f & ST_TEST_PASSED) && pathInliers >= 5) f |= ST_NEED_5PT;  // ptsetreg: count < modelPoints -> fail
+                s.flags = f;
+                sValidSel = 0;
             }
-            hypStart = true;
+            if (slotEnd) slotStart = true;
+            __syncthreads();  // every thread is done with the stage (and sees sValidSel) before it is refilled / reused
+            consLive = k1Next(meta, nSlots, cons);
         }
-        if (slotEnd && threadIdx.x == 0) {
-            SlotState &s = a.state[w];
-            s.testCount = testCount;
-            s.pathInliers = (flags & ST_TEST_PASSED) ? pathInliers : 0u;
-            s.inlierCount = 0;
-            s.tableIdx = a.pairTable[a.pairId[w]];
-            s.pad = sValidSel;  // which bit buffer K2 samples from
-            s.models = 0;
-            s.it = 0;
-            uint32_t f = flags;
-            if ((f & ST_TEST_PASSED) && pathInliers >= 5) f |= ST_NEED_5PT;  // ptsetreg: count < modelPoints -> fail
-            s.flags = f;
-            sValidSel = 0;
-        }
-        if (slotEnd) slotStart = true;
-        __syncthreads();  // every thread is done with the stage (and sees sValidSel) before it is refilled / reused
-        consLive = k1Next(a, cons);
+        // all items of this round were issued and consumed; the descriptors may be overwritten
     }
 }
 
@@ -539,8 +565,9 @@ __global__ void __launch_bounds__(64) k2_fivept_first_solution(WaveArgs a, int o
                     const double4 c = rows[selectRank(bits, nWords, (uint32_t)idx_i)];
                     x1[2 * i] = c.x; x1[2 * i + 1] = c.y; x2[2 * i] = c.z; x2[2 * i + 1] = c.w;
                 }
-                found = (onePairPerWarp ? fivePoint<false, true>(x1, x2, E, 1, 1000, kLegacyDkTolSq, sWs)
-                                        : fivePoint<false>(x1, x2, E, 1, 1000, kLegacyDkTolSq)) > 0;
+                // the RANSAC loop keeps the first solution that has inliers at all, i.e. the first finite one
+                found = (onePairPerWarp ? fivePoint<false, true>(x1, x2, E, 1, 1000, kLegacyDkTolSq, sWs, true)
+                                        : fivePoint<false>(x1, x2, E, 1, 1000, kLegacyDkTolSq, nullptr, true)) > 0;
             }
         }
         if (!(flags & ST_NEED_5PT)) {

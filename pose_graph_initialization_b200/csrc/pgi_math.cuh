@@ -562,8 +562,13 @@ __device__ __forceinline__ int fivePointFront(const double x1[10], const double 
 }
 
 // Back half: every real root z gives (x, y) from the 3x3 system b(z) and the essential matrix x E0 + y E1 + z E2 + E3.
+// firstUsable (the legacy RANSAC of K2): a solution with a NaN entry is skipped.  cv's RANSAC counts, per solution, the
+// correspondences whose error is <= threshold^2 = +inf (ptsetreg.cpp findInliers): every error of a solution with a NaN
+// entry is NaN (all nine entries enter the numerator x2^T E x1), so it has no inliers and can never be kept, while a
+// finite unit-norm solution has them all and ends the loop — "the first solution of the first sample" is really the
+// first FINITE solution (seen once in 44,850 pairs of the sparse benchmark scene).
 __device__ __forceinline__ int fivePointFinish(const double *EE /*4 x 9*/, const double *b /*39*/, const Cx *roots, int n,
-                                               double *Eout, int maxOut)
+                                               double *Eout, int maxOut, bool firstUsable = false)
 {
     int count = 0;
     for (int i = 0; i < n; i++) {
@@ -586,6 +591,14 @@ __device__ __forceinline__ int fivePointFinish(const double *EE /*4 x 9*/, const
             nrm += Ev[k] * Ev[k];
         }
         nrm = sqrt(nrm);
+        if (firstUsable) {
+            bool finite = true;
+            for (int k = 0; k < 9; k++) {
+                const double e = Ev[k] / nrm;
+                finite &= (e == e);
+            }
+            if (!finite) continue;
+        }
         if (count < maxOut)
             for (int k = 0; k < 9; k++) Eout[count * 9 + k] = Ev[k] / nrm;
         count++;
@@ -596,7 +609,7 @@ __device__ __forceinline__ int fivePointFinish(const double *EE /*4 x 9*/, const
 
 template <bool CYCLE_JUMP, bool EXT_WS = false>
 __device__ inline int fivePoint(const double x1[10], const double x2[10], double *Eout, int maxOut, int dkMaxIters,
-                                double dkTolSq, double *ws = nullptr)
+                                double dkTolSq, double *ws = nullptr, bool firstUsable = false)
 {
     double VtL[EXT_WS ? 1 : 81], AL[EXT_WS ? 1 : 200], A1L[EXT_WS ? 1 : 100], invL[EXT_WS ? 1 : 100], bL[EXT_WS ? 1 : 39],
         R6L[EXT_WS ? 1 : 60];
@@ -613,7 +626,7 @@ __device__ inline int fivePoint(const double x1[10], const double x2[10], double
         dkSolveFixed<10, CYCLE_JUMP>(c, roots, dkMaxIters, dkTolSq);
     else
         dkSolveGeneric(c, n, roots, dkMaxIters, dkTolSq);
-    return fivePointFinish(Vt + 45, b, roots, n, Eout, maxOut);
+    return fivePointFinish(Vt + 45, b, roots, n, Eout, maxOut, firstUsable);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -22,6 +22,7 @@ def compare_tuples(checker, scene, log, positions, thr_px=0.4, min_inliers=20, t
     positions = np.asarray(positions, dtype=np.int64)
     positions = positions[np.isin(positions, verifiable_positions(log))]
     bad, first, secs, used = 0, -1, 0.0, 0
+    bad_positions = []
     mix = {"path": 0, "fallback": 0, "rejected": 0}
     for s in range(0, len(positions), chunk):
         pos = positions[s:s + chunk]
@@ -47,7 +48,9 @@ def compare_tuples(checker, scene, log, positions, thr_px=0.4, min_inliers=20, t
             if first < 0:
                 first = int(pos[np.nonzero(~ok)[0][0]])
             bad += int((~ok).sum())
+            bad_positions.extend(int(x) for x in pos[np.nonzero(~ok)[0]][:64])
         mix["path"] += int((success & (info[:, 1] == 1)).sum())
         mix["fallback"] += int((success & (info[:, 1] == 2)).sum())
         mix["rejected"] += int((~success).sum())
-    return dict(tuples=int(len(positions)), mismatches=bad, first_bad=first, seconds=secs, threads=used, **mix)
+    return dict(tuples=int(len(positions)), mismatches=bad, first_bad=first, bad_positions=bad_positions[:64], seconds=secs,
+                threads=used, **mix)

@@ -78,3 +78,14 @@ def test_scene_container_round_trip(tmp_path):
     for k in ("focal", "size", "sim", "kp_offset", "kp", "pair_views", "m_offset", "matches"):
         assert np.array_equal(np.asarray(sc[k]), back[k]), k
     assert np.allclose(np.diag(sc["sim"]), 1.0) and sc["sim"][np.triu_indices(5, 1)].max() < 1.0
+
+
+def test_pyposegraphbuilder_module_is_importable_and_checks_shapes():
+    import numpy as np
+    import pyposegraphbuilder as ppg
+
+    assert ppg.PoseGraphBuilder is not None and callable(ppg.estimate_pose) and callable(ppg.test_pose) and callable(ppg.guided_match)
+    with pytest.raises(ValueError):
+        ppg.estimate_pose(np.zeros((5, 3)), 1e-3)
+    with pytest.raises(ValueError):
+        ppg.test_pose(np.zeros((5, 4)), 1e-3, np.zeros(6))

@@ -20,7 +20,7 @@ def test_guided_match_equals_oracle(engine, oracle, n, seed, bins):
     assert np.array_equal(out["ratios"].view(np.uint64), ref["ratios"].view(np.uint64))
     sel = [(int(a), int(b), float(r)) for (a, b), r in zip(ref["selected_matches"], ref["selected_ratios"])]
     assert out["selected"] == sel
-    if n >= 300:
+    if n >= 1500:
         m = out["matches"]
         assert len(m) > 10 and (d["truth"][m[:, 0]] == m[:, 1]).mean() > 0.95
 
