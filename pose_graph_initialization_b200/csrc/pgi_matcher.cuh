@@ -13,12 +13,14 @@
 //           against 0.75^2, then the 128-D squared descriptor distance (float differences accumulated in double,
 //           matcher.h:371-375), best / second best, count-corrected Lowe ratio (matcher.h:386-406);
 //   phase 4: accepted matches are compacted in source order (block scan).
-// atan2 comes from the CUDA math library: a destination or source keypoint whose scaled angle lies within an ulp of a
-// bin boundary could fall into the neighbouring bin of the host's libm — the parity test counts such cases (none seen).
+// atan2 is evaluated in double-double arithmetic and rounded once (pgi_atan2.h): the correctly rounded value, which is
+// what glibc returns for all but ~2.5e-4 of arguments (CUDA's own atan2 is a 2-ulp function and differed from the host
+// in the angular range of one of five test scenes).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "pgi_atan2.h"
 #include "pgi_math.cuh"
 
 namespace pgi {
@@ -65,7 +67,7 @@ PGI_DEV void mul3(const double *A, const double *B, double *C)
 PGI_DEV double lineAngle(double ny, double nx)
 {
     const double kRadianToDegree = 180.0 / 3.14159265358979323846;
-    double angle = kRadianToDegree * atan2(ny, nx) + 180.0;
+    double angle = kRadianToDegree * pgi_atan::atan2cr(ny, nx) + 180.0;
     if (angle > 180) angle -= 180;
     return angle;
 }
