@@ -195,6 +195,8 @@ struct Visibility {
 static const int kExpandVariant = getenv("PGB_EXPAND") ? atoi(getenv("PGB_EXPAND")) : 2;
 
 struct AStarOut {
+    bool valid = true;        // false: an entry below the cost floor reached the top of the queue (the caller repeats the search without a floor)
+    double minPoppedF = 2.0;  // smallest combined cost among the popped nodes (the start node aside): the floor the search needed
     bool found = false;
     SE3 pose = se3Identity();
     uint32_t touched = 0;
@@ -222,6 +224,7 @@ struct AStarScratch {
     std::vector<uint32_t> mark;  // per-vertex stamp of "expanded in this search"
     uint32_t epoch = 0;
     std::vector<uint32_t> path;
+    uint64_t floorRetries = 0;    // searches repeated because the cost-floor guess was too high
     std::vector<double> childF;   // scratch of one expansion: combined cost / list entry of the admissible children
     std::vector<uint32_t> childE, childMove;
 };
@@ -353,11 +356,35 @@ __attribute__((target("avx2"))) size_t evalEntriesAvx2(const Adj *ra, uint32_t n
 #endif
 
 // AStarTraversal<ImageSimilarityHeuristics>::getPath with the arguments of pose_graph_builder.h:834-841.
+//
+// The open list is std::priority_queue's binary heap, replayed slot by slot (std::push_heap / std::pop_heap of
+// libstdc++: the pop order among equal costs depends on the heap layout, and children of one expansion mostly share
+// their cost) — but ORDERED only where it can matter.  `floorF` is a guess of the smallest cost the
+// search will ever pop.  A child below it takes its slot in the array (slot numbers are what the layout is made of)
+// WITHOUT the climb of std::push_heap.  As long as no such entry reaches the top, every entry >= floorF ("live") sits in
+// exactly the slot the fully ordered queue would give it.  Induction over the queue operations, with the invariant
+// that all ancestors of a live entry are live:
+//   push   a live child climbs while its parent is smaller (std::__push_heap): past every non-live ancestor whatever
+//          their mutual order — they move down the climbed path — and past smaller live ones, which move down one slot
+//          of the path exactly as in the ordered queue; a non-live child cannot displace a live entry;
+//   pop    std::__adjust_heap moves the larger child into the hole level by level (right child on ties): where at least
+//          one child is live the choice is made among live entries by their values, and once both are non-live no live
+//          entry lies underneath (invariant), so the rest of the descent only permutes non-live entries; the entry X of
+//          the last slot is then pushed up from the leaf: a live X passes every non-live entry and every smaller live
+//          entry of the hole's path (they return to the slots they came from) and stops below the first live entry
+//          >= X; a non-live X stays underneath the live part of the path.
+// Which slots hold live entries, and which live entry sits where, is therefore the same as in the ordered queue after
+// every operation, and so is the sequence of popped entries.  In a dense view graph 60-90 % of the children are below
+// anything that is ever popped, and their climbs — random walks through equally irrelevant entries, one mispredicted
+// loop exit each — were ~70 % of the search time.  If an entry below the floor does reach the top, the guess was too
+// high: out.valid = false and the caller repeats the search without a floor (the plain replay).
 void aStar(const GraphView &gv, const double *sim /*transposed*/, uint32_t V, uint32_t from, uint32_t to, size_t maxDepth,
-           double weight, AStarScratch &S, AStarOut &out)
+           double weight, AStarScratch &S, AStarOut &out, double floorF = -1.0)
 {
     const Graph &g = *gv.g;
     out.found = false;
+    out.valid = true;
+    out.minPoppedF = 2.0;
     out.touched = 0;
     out.pushes = 0;
     out.expanded.clear();
@@ -393,6 +420,8 @@ void aStar(const GraphView &gv, const double *sim /*transposed*/, uint32_t V, ui
         if (top.parent == UINT32_MAX) {
             node = ArenaNode{from, UINT32_MAX, 0, UINT32_MAX, 1.0, 0.0};
         } else {
+            if (top.f < floorF) { out.valid = false; return; }  // the floor was a bad guess
+            if (top.f < out.minPoppedF) out.minPoppedF = top.f;
             const ArenaNode &pn = S.arena[top.parent];
             const Adj &e = entryAt(pn.listOwner, top.entry);
             uint32_t next = e.next;
@@ -483,12 +512,13 @@ void aStar(const GraphView &gv, const double *sim /*transposed*/, uint32_t V, ui
                     const double nextToDest = c1 < h ? h : c1;
                     const double combined = wgt * edgeCost + oneMinusWeight * nextToDest;
                     size_t hole = hs++;
-                    while (hole > 0) {
-                        const size_t parent = (hole - 1) / 2;
-                        if (!(first[parent].f < combined)) break;
-                        first[hole] = first[parent];
-                        hole = parent;
-                    }
+                    if (combined >= floorF)
+                        while (hole > 0) {
+                            const size_t parent = (hole - 1) / 2;
+                            if (!(first[parent].f < combined)) break;
+                            first[hole] = first[parent];
+                            hole = parent;
+                        }
                     first[hole] = HeapItem{combined, ni, ent};
                 };
                 for (; entry < nr; ++entry) push1(ra[entry], entry);
@@ -520,7 +550,7 @@ void aStar(const GraphView &gv, const double *sim /*transposed*/, uint32_t V, ui
                     const size_t slot = hs + i;
                     first[slot] = HeapItem{cf[i], ni, ce[i]};
                     mv[nMove] = (uint32_t)i;
-                    nMove += first[(slot - 1) / 2].f < cf[i] ? 1 : 0;  // slot >= 1 here (hs >= cnt >= 1)
+                    nMove += (first[(slot - 1) / 2].f < cf[i]) & (cf[i] >= floorF) ? 1 : 0;  // slot >= 1 here (hs >= cnt >= 1)
                 }
                 for (size_t k = 0; k < nMove; k++) {
                     const size_t i = mv[k];
@@ -539,12 +569,13 @@ void aStar(const GraphView &gv, const double *sim /*transposed*/, uint32_t V, ui
                 for (size_t i = 0; i < cnt; i++) {
                     const double combined = cf[i];
                     size_t hole = hs++;
-                    while (hole > 0) {
-                        const size_t parent = (hole - 1) / 2;
-                        if (!(first[parent].f < combined)) break;
-                        first[hole] = first[parent];
-                        hole = parent;
-                    }
+                    if (combined >= floorF)
+                        while (hole > 0) {
+                            const size_t parent = (hole - 1) / 2;
+                            if (!(first[parent].f < combined)) break;
+                            first[hole] = first[parent];
+                            hole = parent;
+                        }
                     first[hole] = HeapItem{combined, ni, ce[i]};
                 }
             out.pushes += (uint32_t)(hs - hs0);
@@ -580,6 +611,7 @@ struct Item {
     SE3 hyp = se3Identity();
     std::vector<uint32_t> expanded;
     uint32_t touched = 0, pushes = 0;
+    double floorSeen = -1.0;  // smallest cost the position's last search popped (< 0: none yet): the next search's floor guess
     bool needGpu = false;
     Outcome pred;             // what the overlay currently assumes for this position
     const pgi_verdict *finalV = nullptr, *pathV = nullptr;
@@ -719,6 +751,7 @@ struct pgb_builder {
     bool ovDirty = true;         // the overlay changed since it was last mirrored to the device
     double hybridShare = 0.3;    // share of a round's estimated search work the host pool takes beside the device (0: none)
     uint32_t gpuBudget = 0;      // push budget of the round's device queries (0: unlimited)
+    std::vector<double> srcFloor, dstFloor;  // per view: smallest popped cost of the last search from / to it (floor guesses)
     std::vector<uint32_t> srcCost;  // per source view: pushes of the last search that started there (cost estimate)
     double meanCost = 0.0;       // running mean of pushes per search
     std::vector<pgi_adj_entry> gpuEntries, commitEntries;
@@ -821,6 +854,9 @@ void rebuildOverlay(pgb_builder *b, uint32_t from = 0)
     b->ctr.sec_visibility += nowSec() - t0;
 }
 
+// Margin under the remembered floors for the next guess; PGB_FLOOR_MARGIN < 0 switches the cost floor off.
+static const double kFloorMargin = getenv("PGB_FLOOR_MARGIN") ? atof(getenv("PGB_FLOOR_MARGIN")) : 0.01;
+
 void searchPosition(pgb_builder *b, uint32_t k, AStarScratch &S)
 {
     Item &it = b->wave[k];
@@ -830,8 +866,28 @@ void searchPosition(pgb_builder *b, uint32_t k, AStarScratch &S)
     if (b->cfg.use_path_finding && it.visible && !it.staticSkip && !it.dupSkip) {  // :569-570
         AStarOut o;
         GraphView gv{&b->graph, &b->overlay, k};
+        // Cost-floor guess (see aStar): what this position's previous search needed, else what the last searches from the
+        // same source view and to the same destination view needed (neighbouring queue positions behave alike), minus a
+        // margin.  The tables are hints shared by the pool threads without synchronisation — any value is a valid guess.
+        double floorF = -1.0;
+        if (kFloorMargin >= 0.0) {
+            double g = it.floorSeen;
+            if (g < 0.0 && b->srcFloor[it.src] >= 0.0 && b->dstFloor[it.dst] >= 0.0) g = std::min(b->srcFloor[it.src], b->dstFloor[it.dst]);
+            if (g >= 0.0) floorF = g - kFloorMargin;
+        }
         aStar(gv, b->sim.data(), b->V, it.src, it.dst, (size_t)b->cfg.maximum_search_depth,
-              b->cfg.traversal_heuristics_weight, S, o);
+              b->cfg.traversal_heuristics_weight, S, o, floorF);
+        if (!o.valid && floorF - 0.05 > 0.0) {  // guessed too high: once more with a wide margin, then without a floor
+            S.floorRetries++;
+            aStar(gv, b->sim.data(), b->V, it.src, it.dst, (size_t)b->cfg.maximum_search_depth,
+                  b->cfg.traversal_heuristics_weight, S, o, floorF - 0.05);
+        }
+        if (!o.valid) {
+            S.floorRetries++;
+            aStar(gv, b->sim.data(), b->V, it.src, it.dst, (size_t)b->cfg.maximum_search_depth,
+                  b->cfg.traversal_heuristics_weight, S, o);
+        }
+        if (o.minPoppedF <= 1.0) it.floorSeen = b->srcFloor[it.src] = b->dstFloor[it.dst] = o.minPoppedF;
         it.hasHyp = o.found;
         it.hyp = o.pose;
         it.expanded.swap(o.expanded);
@@ -1260,6 +1316,8 @@ int32_t pgb_create(const pgb_config *cfg, uint64_t n_views, const double *sim, u
     b->overlay.byVertex.resize(n_views);
     b->vis.init((uint32_t)n_views);
     b->minChangedPos.assign(n_views, UINT32_MAX);
+    b->srcFloor.assign(n_views, -1.0);
+    b->dstFloor.assign(n_views, -1.0);
     b->fbCache.resize(n_pairs);
     b->fbHave.assign(n_pairs, 0);
     memset(&b->ctr, 0, sizeof b->ctr);
@@ -1535,7 +1593,12 @@ void pgb_copy_edges(pgb_builder *b, pgb_edge *out)
 }
 uint64_t pgb_log_count(pgb_builder *b) { return b ? b->log.size() : 0; }
 void pgb_copy_log(pgb_builder *b, pgb_log *out) { memcpy(out, b->log.data(), b->log.size() * sizeof(pgb_log)); }
-void pgb_get_counters(pgb_builder *b, pgb_counters *out) { *out = b->ctr; }
+void pgb_get_counters(pgb_builder *b, pgb_counters *out)
+{
+    *out = b->ctr;
+    out->floor_retries = 0;
+    for (const AStarScratch &s : b->scratch) out->floor_retries += s.floorRetries;
+}
 
 int32_t pgb_astar(pgb_builder *b, uint32_t src, uint32_t dst, double *hyp_q_t, uint32_t *touched_nodes)
 {

@@ -3,7 +3,8 @@
 // queue positions on that fixed graph with T threads and reports time, pops and pushes, plus a checksum of the results
 // so that two builds can be compared.
 //   g++ -O3 -ffp-contract=off -pthread -I include -o /tmp/astar_micro scripts/astar_micro.cpp
-//   /tmp/astar_micro sim1000.bin 1000 300000 4096 8
+//   /tmp/astar_micro sim1000.bin 1000 300000 4096 8 [margin]     (margin >= 0: cost floor = last floor seen for the
+//                                                                  source / destination view - margin; default: no floor)
 #include "../pose_graph_initialization_b200/csrc/pgb_host.cpp"
 #include <cstdio>
 #include <cstdlib>
@@ -20,6 +21,9 @@ int main(int argc, char **argv)
     const uint32_t V = (uint32_t)atoi(argv[2]);
     const size_t M = (size_t)atol(argv[3]), K = (size_t)atol(argv[4]);
     const int T = atoi(argv[5]);
+    const double margin = argc > 6 ? atof(argv[6]) : -1.0;
+    std::vector<double> srcFloor(V, -1.0), dstFloor(V, -1.0);
+    std::atomic<uint64_t> retries(0);
     std::vector<double> sim((size_t)V * V);
     FILE *f = fopen(argv[1], "rb");
     if (!f || fread(sim.data(), 8, sim.size(), f) != sim.size()) return 2;
@@ -62,7 +66,15 @@ int main(int argc, char **argv)
             const size_t i = next.fetch_add(1);
             if (i >= Kx) break;
             GraphView gv{&b->graph, nullptr, 0};
-            aStar(gv, b->sim.data(), V, b->order[Mx + i].first, b->order[Mx + i].second, 5, 0.8, b->scratch[tid], outs[i]);
+            const uint32_t s = b->order[Mx + i].first, d = b->order[Mx + i].second;
+            double floorF = -1.0;
+            if (margin >= 0.0 && srcFloor[s] >= 0.0 && dstFloor[d] >= 0.0) floorF = std::min(srcFloor[s], dstFloor[d]) - margin;
+            aStar(gv, b->sim.data(), V, s, d, 5, 0.8, b->scratch[tid], outs[i], floorF);
+            if (!outs[i].valid) {
+                ++retries;
+                aStar(gv, b->sim.data(), V, s, d, 5, 0.8, b->scratch[tid], outs[i]);
+            }
+            if (outs[i].minPoppedF <= 1.0) srcFloor[s] = dstFloor[d] = outs[i].minPoppedF;
             pops[tid] += outs[i].touched;
             pushes[tid] += outs[i].pushes;
         }
@@ -74,8 +86,8 @@ int main(int argc, char **argv)
         cs = mix(cs ^ outs[i].touched) ^ mix(outs[i].pushes + 77) ^ (outs[i].found ? 1 : 0);
         for (uint32_t v : outs[i].expanded) cs = mix(cs + v);
     }
-    printf("M=%zu K=%zu T=%d  %.3f s  searches/s %.0f  pops %llu (%.0f/search)  pushes %llu (%.0f/search)  %.2f ns/push/thread  checksum %016llx\n",
+    printf("M=%zu K=%zu T=%d  %.3f s  searches/s %.0f  pops %llu (%.0f/search)  pushes %llu (%.0f/search)  %.2f ns/push/thread  retries %llu  checksum %016llx\n",
            Mx, Kx, T, dt, Kx / dt, (unsigned long long)tp, (double)tp / Kx, (unsigned long long)tq, (double)tq / Kx,
-           dt * T / (double)tq * 1e9, (unsigned long long)cs);
+           dt * T / (double)tq * 1e9, (unsigned long long)retries.load(), (unsigned long long)cs);
     return 0;
 }
