@@ -94,6 +94,7 @@ typedef struct pgb_counters {
     double sec_search_gpu;      /* wall time inside the device backend                                   */
     double sec_search_host_part;/* wall time of the host pool's share of device rounds (runs beside the device) */
     uint64_t floor_retries;     /* host searches repeated because their cost-floor guess was too high (pgb_host.cpp: aStar) */
+    uint64_t stale_spared;      /* search results kept although an expanded vertex gained a changed edge (fine staleness rule) */
 } pgb_counters;
 
 /* sim: V x V row-major similarity matrix (the text file of imagesimilarity_graph.h:108-171 already parsed).

@@ -47,7 +47,7 @@ class PgbCounters(C.Structure):
                                           "astar_reruns", "verdict_cache_hits", "astar_pops", "astar_pushes")] + \
                [(k, C.c_double) for k in ("sec_astar", "sec_commit", "sec_visibility")] + \
                [(k, C.c_uint64) for k in ("gpu_searches", "gpu_search_redo", "search_mismatches")] + \
-               [("sec_search_gpu", C.c_double), ("sec_search_host_part", C.c_double), ("floor_retries", C.c_uint64)]
+               [("sec_search_gpu", C.c_double), ("sec_search_host_part", C.c_double), ("floor_retries", C.c_uint64), ("stale_spared", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -202,6 +202,7 @@ struct AStarOut {
     uint32_t touched = 0;
     uint32_t pushes = 0;
     std::vector<uint32_t> expanded;  // vertices whose edge lists were read
+    std::vector<double> expCost;     // (c0, c1) of the node at each of those expansions: what a child's cost is computed from
 };
 
 // Heap entries describe a child lazily: (parent node, entry of the parent's edge list).  The child's vertex and
@@ -355,6 +356,44 @@ __attribute__((target("avx2"))) size_t evalEntriesAvx2(const Adj *ra, uint32_t n
 }
 #endif
 
+#ifdef PGB_HAVE_AVX2_PATH
+// The same pass eight entries at a time where the CPU has AVX-512 (compress stores replace the scalar compaction).
+static const bool kUseAvx512 = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512vl") &&
+                               !(getenv("PGB_NO_AVX512") && atoi(getenv("PGB_NO_AVX512")) != 0);
+__attribute__((target("avx512f,avx512vl,avx2"))) size_t evalEntriesAvx512(const Adj *ra, uint32_t n, const uint32_t *mark, uint32_t epoch,
+                                                                         const double *simTo, double c0, double c1, double wgt,
+                                                                         double omw, double *cf, uint32_t *ce, size_t cnt,
+                                                                         uint32_t &entryOut)
+{
+    const __m512d vc0 = _mm512_set1_pd(c0), vc1 = _mm512_set1_pd(c1), vw = _mm512_set1_pd(wgt), vo = _mm512_set1_pd(omw);
+    const __m512d zero = _mm512_setzero_pd();
+    const __m256i vep = _mm256_set1_epi32((int)epoch);
+    const __m512i idxScore = _mm512_setr_epi64(1, 3, 5, 7, 9, 11, 13, 15), idxHead = _mm512_setr_epi64(0, 2, 4, 6, 8, 10, 12, 14);
+    __m256i vent = _mm256_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7);
+    const __m256i eight = _mm256_set1_epi32(8);
+    uint32_t e = 0;
+    for (; e + 8 <= n; e += 8) {
+        // Adj = {u32 next, u32 edge, f64 score}: two 64-byte loads hold entries e..e+3 and e+4..e+7
+        const __m512d a0 = _mm512_loadu_pd(reinterpret_cast<const double *>(ra + e));
+        const __m512d a1 = _mm512_loadu_pd(reinterpret_cast<const double *>(ra + e + 4));
+        const __m512d sc = _mm512_permutex2var_pd(a0, idxScore, a1);
+        const __m256i nx = _mm512_cvtepi64_epi32(_mm512_castpd_si512(_mm512_permutex2var_pd(a0, idxHead, a1)));  // low halves: next
+        const __m256i mk = _mm256_i32gather_epi32(reinterpret_cast<const int *>(mark), nx, 4);
+        const __m512d h = _mm512_i32gather_pd(nx, simTo, 8);
+        const __m512d ec = _mm512_mask_blend_pd(_mm512_cmp_pd_mask(vc0, sc, _CMP_GT_OQ), vc0, sc);  // c0 > score ? score : c0
+        const __m512d nd = _mm512_mask_blend_pd(_mm512_cmp_pd_mask(vc1, h, _CMP_LT_OQ), vc1, h);    // c1 < h ? h : c1
+        const __m512d f = _mm512_add_pd(_mm512_mul_pd(vw, ec), _mm512_mul_pd(vo, nd));
+        const __mmask8 ok = (__mmask8)(~_mm512_cmp_pd_mask(sc, zero, _CMP_LT_OQ)) & _mm256_cmpneq_epi32_mask(mk, vep);
+        _mm512_mask_compressstoreu_pd(cf + cnt, ok, f);
+        _mm256_mask_compressstoreu_epi32(ce + cnt, ok, vent);
+        cnt += (size_t)__builtin_popcount(ok);
+        vent = _mm256_add_epi32(vent, eight);
+    }
+    entryOut = e;
+    return cnt;
+}
+#endif
+
 // AStarTraversal<ImageSimilarityHeuristics>::getPath with the arguments of pose_graph_builder.h:834-841.
 //
 // The open list is std::priority_queue's binary heap, replayed slot by slot (std::push_heap / std::pop_heap of
@@ -388,6 +427,7 @@ void aStar(const GraphView &gv, const double *sim /*transposed*/, uint32_t V, ui
     out.touched = 0;
     out.pushes = 0;
     out.expanded.clear();
+    out.expCost.clear();
     if (S.mark.size() != V) { S.mark.assign(V, 0); S.epoch = 0; }
     if (++S.epoch == 0) { std::fill(S.mark.begin(), S.mark.end(), 0); S.epoch = 1; }
     S.arena.clear();
@@ -453,7 +493,11 @@ void aStar(const GraphView &gv, const double *sim /*transposed*/, uint32_t V, ui
         S.mark[v] = epoch;  // nodeStates[v] = Open  :814
         // `expanded` = the vertices whose edge lists this search ITERATED (:820-866): what a later graph change must touch
         // to invalidate the result.  A node popped at the maximum depth is marked but pushes nothing.
-        if (node.depth < maxDepth) out.expanded.push_back(v);
+        if (node.depth < maxDepth) {
+            out.expanded.push_back(v);
+            out.expCost.push_back(node.c0);
+            out.expCost.push_back(node.c1);
+        }
         const std::vector<Adj> &real = g.byVertex[v];
         const std::vector<OvAdj> *ovl = gv.ov ? &gv.ov->byVertex[v] : nullptr;
         const bool hasOv = ovl && !ovl->empty() && (*ovl)[0].pos < gv.cutoff;
@@ -482,7 +526,7 @@ void aStar(const GraphView &gv, const double *sim /*transposed*/, uint32_t V, ui
             // in list order.  Same operations on the same operands as the one-pass loop, but the sift-up's unpredictable
             // exit no longer sits between two gathers.
             const size_t listLen = rl.size() + (ol ? ol->size() : 0);
-            if (S.childF.size() < listLen) { S.childF.resize(listLen); S.childE.resize(listLen); }
+            if (S.childF.size() < listLen + 8) { S.childF.resize(listLen + 8); S.childE.resize(listLen + 8); }  // (+8: a compress store may be issued at the very end)
             double *cf = S.childF.data();
             uint32_t *ce = S.childE.data();
             size_t cnt = 0;
@@ -531,7 +575,8 @@ void aStar(const GraphView &gv, const double *sim /*transposed*/, uint32_t V, ui
                 continue;
             }
 #ifdef PGB_HAVE_AVX2_PATH
-            if (kExpandVariant >= 2 && kUseAvx2 && lv == v) cnt = evalEntriesAvx2(ra, nr, mark, epoch, simTo, c0, c1, wgt, oneMinusWeight, cf, ce, cnt, entry);
+            if (kExpandVariant >= 2 && kUseAvx512 && lv == v) cnt = evalEntriesAvx512(ra, nr, mark, epoch, simTo, c0, c1, wgt, oneMinusWeight, cf, ce, cnt, entry);
+            else if (kExpandVariant >= 2 && kUseAvx2 && lv == v) cnt = evalEntriesAvx2(ra, nr, mark, epoch, simTo, c0, c1, wgt, oneMinusWeight, cf, ce, cnt, entry);
 #endif
             for (; entry < nr; ++entry) eval(ra[entry], entry);
             if (ol)
@@ -610,6 +655,8 @@ struct Item {
     bool hasHyp = false;
     SE3 hyp = se3Identity();
     std::vector<uint32_t> expanded;
+    std::vector<double> expCost;  // (c0, c1) per entry of `expanded` (empty: not recorded, e.g. a device search)
+    double tauMin = 2.0;          // smallest cost the current search result popped (2: nothing but the start node)
     uint32_t touched = 0, pushes = 0;
     double floorSeen = -1.0;  // smallest cost the position's last search popped (< 0: none yet): the next search's floor guess
     bool needGpu = false;
@@ -619,6 +666,14 @@ struct Item {
     bool remoteKnown = false; // a record of the owner has been imported
     pgi_verdict remoteV;      // the owner's path verdict for the position (remote positions only)
 };
+
+struct Change {  // a wave position whose actual outcome differs from the prediction the overlay was built from
+    uint32_t k, u, w;
+    bool existence;      // the edge appears or disappears (otherwise only its score / pose changes)
+    double sOld, sNew;   // inlier ratios of the predicted and of the actual edge
+};
+// PGB_FINE_STALENESS=0: a changed edge at an expanded vertex always invalidates the search (the coarse rule)
+static const bool kFineStaleness = !(getenv("PGB_FINE_STALENESS") && atoi(getenv("PGB_FINE_STALENESS")) == 0);
 
 struct HypKey {
     uint32_t pair;
@@ -735,6 +790,8 @@ struct pgb_builder {
     int phase = 0;                 // 0 search/resolve, 1 waiting for the record exchange, 2 compare
     int status = 0;                // PGB_WAVE_* of the open wave
     std::vector<uint32_t> minChangedPos;  // per vertex: smallest wave position whose outcome changed this round
+    std::vector<Change> changes;          // the round's changed positions, in position order
+    std::vector<std::vector<uint32_t>> changesOf;  // per vertex: indices into `changes` of the edges touching it
     std::vector<pgi_verdict> fbCache;
     std::vector<uint8_t> fbHave;
     std::unordered_map<HypKey, PathVerdict, HypKeyHash> pathCache;
@@ -862,6 +919,8 @@ void searchPosition(pgb_builder *b, uint32_t k, AStarScratch &S)
     Item &it = b->wave[k];
     it.hasHyp = false;
     it.expanded.clear();
+    it.expCost.clear();
+    it.tauMin = 2.0;
     it.touched = it.pushes = 0;
     if (b->cfg.use_path_finding && it.visible && !it.staticSkip && !it.dupSkip) {  // :569-570
         AStarOut o;
@@ -891,6 +950,8 @@ void searchPosition(pgb_builder *b, uint32_t k, AStarScratch &S)
         it.hasHyp = o.found;
         it.hyp = o.pose;
         it.expanded.swap(o.expanded);
+        it.expCost.swap(o.expCost);
+        it.tauMin = o.minPoppedF;
         it.touched = o.touched;
         it.pushes = o.pushes;
     }
@@ -980,6 +1041,7 @@ int32_t searchOnDevice(pgb_builder *b, const std::vector<uint32_t> &todo, std::v
         it.touched = r.touched;
         it.pushes = r.pushes;
         it.expanded.clear();
+        it.expCost.clear();  // not recorded by the device search: the coarse staleness rule applies
         const uint32_t *bits = b->gpuBits.data() + (size_t)i * words;
         for (uint32_t w = 0; w < words; w++) {
             uint32_t x = bits[w];
@@ -1225,12 +1287,17 @@ uint32_t advanceWave(pgb_builder *b)
         std::fill(b->minChangedPos.begin(), b->minChangedPos.end(), UINT32_MAX);
         uint32_t firstChanged = UINT32_MAX;
         bool allKnown = true;
+        b->changes.clear();
         for (uint32_t k = 0; k < n; k++) {
             Item &it = b->wave[k];
             if (it.staticSkip || it.dupSkip) continue;
             if (it.mine ? !it.searched : !it.remoteKnown) { allKnown = false; continue; }
             const Outcome act = outcomeOf(it.finalV);
             if (!act.sameEdge(it.pred)) {
+                const bool hadEdge = it.pred.known && it.pred.accepted;
+                b->changes.push_back(Change{k, it.src, it.dst, hadEdge != act.accepted,
+                                            hadEdge ? (double)it.pred.inliers / (double)it.nCorr : 0.0,
+                                            act.accepted ? (double)act.inliers / (double)it.nCorr : 0.0});
                 it.pred = act;
                 if (firstChanged == UINT32_MAX) firstChanged = k;
                 b->minChangedPos[it.src] = std::min(b->minChangedPos[it.src], k);
@@ -1244,11 +1311,46 @@ uint32_t advanceWave(pgb_builder *b)
             continue;             // nothing changed among the known positions: keep searching
         }
         ++b->rounds;
-        for (uint32_t m = firstChanged + 1; m < n; m++) {
-            Item &it = b->wave[m];
-            if (!it.mine || !it.searched) continue;
-            for (uint32_t v : it.expanded)
-                if (b->minChangedPos[v] < m) { it.searched = false; break; }
+        // Which search results does the round invalidate?  A search reads the edge lists of the vertices it expanded
+        // (graph_traversal.h:817) and nothing else, so position m can only be affected by a changed position k < m whose
+        // edge touches one of them.  If the edge merely changed its score (or pose), the finer rule of the cost floor
+        // applies (aStar): the child that expansion pushed through the edge has a combined cost computed from the node's
+        // (c0, c1) and the score; if it is below the smallest cost the search ever popped (tauMin) under the predicted AND
+        // under the actual score, it was and remains an entry that never leaves the queue and whose value decides
+        // nothing — the search is bit for bit the same.  An edge that appears or disappears shifts the slots of the
+        // children behind it and always invalidates.
+        if (!b->changes.empty()) {
+            for (std::vector<uint32_t> &l : b->changesOf) l.clear();
+            if (b->changesOf.size() != b->V) b->changesOf.assign(b->V, {});
+            for (uint32_t ci = 0; ci < b->changes.size(); ci++) {
+                b->changesOf[b->changes[ci].u].push_back(ci);
+                b->changesOf[b->changes[ci].w].push_back(ci);
+            }
+            const double wgt = b->cfg.traversal_heuristics_weight, omw = 1.0 - wgt;
+            for (uint32_t m = firstChanged + 1; m < n; m++) {
+                Item &it = b->wave[m];
+                if (!it.mine || !it.searched) continue;
+                const bool fine = kFineStaleness && it.expCost.size() == 2 * it.expanded.size();
+                const double *simTo = b->sim.data() + (size_t)it.dst * b->V;
+                for (size_t x = 0; x < it.expanded.size() && it.searched; x++) {
+                    const uint32_t v = it.expanded[x];
+                    if (b->minChangedPos[v] >= m) continue;
+                    if (!fine) { it.searched = false; break; }
+                    const double c0 = it.expCost[2 * x], c1 = it.expCost[2 * x + 1];
+                    for (uint32_t ci : b->changesOf[v]) {
+                        const Change &c = b->changes[ci];
+                        if (c.k >= m) break;  // (lists are in position order)
+                        if (c.existence) { it.searched = false; break; }
+                        const uint32_t other = c.u == v ? c.w : c.u;
+                        const double h = simTo[other];
+                        const double nd = c1 < h ? h : c1;
+                        const double fOld = wgt * (c0 > c.sOld ? c.sOld : c0) + omw * nd;  // graph_traversal.h:843-852
+                        const double fNew = wgt * (c0 > c.sNew ? c.sNew : c0) + omw * nd;
+                        if (!(fOld < it.tauMin) || !(fNew < it.tauMin)) { it.searched = false; break; }
+                    }
+                }
+                if (it.searched) ++b->ctr.stale_spared;  // (counts positions that were examined and kept)
+            }
         }
         rebuildOverlay(b, firstChanged);
     }

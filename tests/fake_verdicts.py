@@ -26,6 +26,7 @@ def _unit_pose(h):
 
 
 FB_SCORE = [0.55, 0.10]  # fallback inlier ratio: base, spread (module-level knob of the benchmark script)
+PATH_SCORE = []          # path-branch inlier ratio [base, spread]; empty: ~1.0 (the benchmark script sets the measured mix)
 
 
 def fake_verdicts(items, n_corr, path_ratio=3, fallback=True):
@@ -51,6 +52,8 @@ def fake_verdicts(items, n_corr, path_ratio=3, fallback=True):
     v["accepted"] = 1
     v["branch"] = np.where(path_ok, 1, 2)
     inl_path = n_corr - (hh % np.uint64(max(1, n_corr // 100))).astype(np.uint32)
+    if PATH_SCORE:
+        inl_path = (PATH_SCORE[0] * n_corr + (hh % np.uint64(max(1, int(n_corr * PATH_SCORE[1]))))).astype(np.uint32)
     inl_fb = (FB_SCORE[0] * n_corr + (hp % np.uint64(max(1, int(n_corr * FB_SCORE[1]))))).astype(np.uint32)
     v["inlier_count"] = np.where(path_ok, inl_path, inl_fb)
     v["path_inliers"] = np.where(path_ok, inl_path, 0)
