@@ -177,6 +177,22 @@ void pgb_get_counters(pgb_builder *b, pgb_counters *out);
 /* Stand-alone A* on the builder's current graph (testing). Returns 1 if a hypothesis was composed. */
 int32_t pgb_astar(pgb_builder *b, uint32_t src, uint32_t dst, double *hyp_q_t, uint32_t *touched_nodes);
 
+/* ---- Tracklets (point_track.h:541-712): multi-view point tracks built from verified matches ------------------------
+ * Replaces reconstruction::Tracklets for the quick-matching branch of processImages (pose_graph_builder.h:492-520 reads
+ * them, :663-676 / :697-703 feed them).  Not thread-safe by itself: the reference serialises add() behind a writer lock
+ * and the wave host commits in order from one thread.  Keypoint indices are the caller's (cv::DMatch query/train idx). */
+typedef struct pgb_tracklets pgb_tracklets;
+pgb_tracklets *pgb_tracklets_create(uint64_t view_number);
+void pgb_tracklets_destroy(pgb_tracklets *t);
+/* Tracklets::add(imageIdxSource, imageIdxDestination, matches, inlierMask)  point_track.h:638-712.  0, or -1 on null input. */
+int32_t pgb_tracklets_add(pgb_tracklets *t, uint64_t view_src, uint64_t view_dst, uint64_t n, const uint64_t *point_src,
+                          const uint64_t *point_dst, const uint8_t *inlier_mask);
+/* Tracklets::getCorrespondences(matches, viewIdSource, viewIdDestination, maximumCorrespondenceNumber)  :575-636.
+ * Returns the number of matches written (up to maximum + 1, as the reference), -1 if `capacity` is too small. */
+int64_t pgb_tracklets_get_correspondences(pgb_tracklets *t, uint64_t view_src, uint64_t view_dst, uint64_t maximum,
+                                          uint64_t *out_src, uint64_t *out_dst, uint64_t capacity);
+uint64_t pgb_tracklets_track_count(pgb_tracklets *t);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,7 +61,8 @@ PGB_EXPORTS = ["pgb_create", "pgb_destroy", "pgb_remaining", "pgb_set_fallback_v
                "pgb_queue_size", "pgb_queue_pairs", "pgb_set_partition", "pgb_wave_status", "pgb_wave_size", "pgb_run_wave",
                "pgb_export_records", "pgb_import_records", "pgb_next_wave", "pgb_set_search_backend", "pgb_copy_sim_table",
                "pgb_commit_wave", "pgb_edge_count", "pgb_copy_edges", "pgb_log_count", "pgb_copy_log", "pgb_get_counters",
-               "pgb_astar"]
+               "pgb_astar", "pgb_tracklets_create", "pgb_tracklets_destroy", "pgb_tracklets_add",
+               "pgb_tracklets_get_correspondences", "pgb_tracklets_track_count"]
 
 
 def _host_lib():
@@ -82,6 +83,10 @@ def _host_lib():
         lib.pgb_wave_status.restype = C.c_int32
         lib.pgb_set_partition.restype = C.c_int32
         lib.pgb_set_search_backend.restype = C.c_int32
+        lib.pgb_tracklets_create.restype = C.c_void_p
+        lib.pgb_tracklets_add.restype = C.c_int32
+        lib.pgb_tracklets_get_correspondences.restype = C.c_int64
+        lib.pgb_tracklets_track_count.restype = C.c_uint64
         for name in PGB_EXPORTS[1:]:
             getattr(lib, name).argtypes = None
         lib._pgb_ready = True
@@ -94,6 +99,49 @@ def _ptr(a):
 
 class DriveStats(C.Structure):
     _fields_ = [("engine_s", C.c_double), ("host_s", C.c_double), ("rounds", C.c_uint32), ("items", C.c_uint32)]
+
+
+class Tracklets:
+    """reconstruction::Tracklets (point_track.h:541-712) behind pgb_tracklets_*: `add(src, dst, matches, inlierMask)` and
+    `getCorrespondences(src, dst, maximum)` with the reference's argument meaning (matches = (srcIdx, dstIdx[, value])
+    rows; the returned rows carry the value 0.0 the reference leaves in the third tuple member)."""
+
+    def __init__(self, viewNumber_):
+        self.lib = _host_lib()
+        self.h = C.c_void_p(self.lib.pgb_tracklets_create(C.c_uint64(int(viewNumber_))))
+        if not self.h:
+            raise MemoryError("pgb_tracklets_create failed")
+
+    def close(self):
+        if self.h:
+            self.lib.pgb_tracklets_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def add(self, imageIdxSource_, imageIdxDestination_, matches_, inlierMask_):
+        m = np.asarray(matches_, dtype=np.float64).reshape(-1, np.shape(matches_)[1] if len(matches_) else 2)
+        src = np.ascontiguousarray(m[:, 0], dtype=np.uint64)
+        dst = np.ascontiguousarray(m[:, 1], dtype=np.uint64)
+        mask = np.ascontiguousarray(inlierMask_, dtype=np.uint8)
+        if len(mask) != len(src):
+            raise ValueError("inlierMask_ must have one entry per match")
+        rc = self.lib.pgb_tracklets_add(self.h, C.c_uint64(int(imageIdxSource_)), C.c_uint64(int(imageIdxDestination_)),
+                                        C.c_uint64(len(src)), _ptr(src), _ptr(dst), _ptr(mask))
+        if rc != 0:
+            raise RuntimeError("pgb_tracklets_add failed")
+
+    def getCorrespondences(self, viewIdSource_, viewIdDestination_, maximumCorrespondenceNumber_):
+        cap = int(maximumCorrespondenceNumber_) + 1
+        a, b = np.zeros(cap, dtype=np.uint64), np.zeros(cap, dtype=np.uint64)
+        n = self.lib.pgb_tracklets_get_correspondences(self.h, C.c_uint64(int(viewIdSource_)), C.c_uint64(int(viewIdDestination_)),
+                                                       C.c_uint64(int(maximumCorrespondenceNumber_)), _ptr(a), _ptr(b), C.c_uint64(cap))
+        if n < 0:
+            raise RuntimeError("pgb_tracklets_get_correspondences failed")
+        return [(int(a[i]), int(b[i]), 0.0) for i in range(n)]
+
+    def track_count(self):
+        return int(self.lib.pgb_tracklets_track_count(self.h))
 
 
 class HostBuilder:
@@ -319,11 +367,13 @@ class RecordExchanger:
 
 
 def default_wave_size(n_views, world_size=1, gpu_search=False):
-    """Queue positions per speculative wave.  Host-pool searches: 256 on one GPU (fewest re-searches: measured optimum on
-    cfg2 and cfg3), 512 with several ranks (every round of a wave costs a record exchange).  Device searches (K6) need
-    large rounds to fill the GPU: 2048 (at the price of ~1.6x the searches)."""
+    """Queue positions per speculative wave.  Host-pool searches: 256 on one GPU (fewest searches; the step is bound by
+    the GPU's fallback work there, not by the rounds), 1024 with several ranks: every round of a wave costs an engine
+    round trip and a record exchange that do not shrink with the rank count, and since the fine staleness rule
+    (pgb_host.cpp) a 4x longer wave needs 63 % fewer rounds for 43 % more searches.  Device searches (K6) need large
+    rounds to fill the GPU: 2048."""
     if not gpu_search:
-        return 256 if world_size == 1 else 512
+        return 256 if world_size == 1 else 1024
     return 1024 if n_views < 600 else 2048
 
 

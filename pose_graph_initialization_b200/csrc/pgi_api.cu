@@ -433,6 +433,19 @@ pgi_status submitWave(pgi_ctx *ctx, const Registration &r, uint32_t n, const uin
     return PGI_OK;
 }
 
+// A failed CUDA call inside a wait must not leave the context "in flight" for ever (every later submit would answer
+// PGI_ERR_STATE): whatever the exit path, the wave is over once the wait returns.
+struct WaveEndGuard {
+    pgi_ctx *ctx;
+    ~WaveEndGuard()
+    {
+        if (ctx->inFlight) {
+            cudaStreamSynchronize(ctx->stream);  // best effort: nothing of the failed wave may still be running
+            ctx->inFlight = false;
+        }
+    }
+};
+
 pgi_status finishWave(pgi_ctx *ctx)
 {
     // caller has synchronised the stream
@@ -679,6 +692,7 @@ pgi_status pgi_wait_wave(pgi_ctx *ctx, pgi_verdict *out, uint8_t *masks_or_null)
 {
     if (!ctx) return PGI_ERR_INVALID;
     if (!ctx->inFlight) { ctx->err = "no wave in flight"; return PGI_ERR_STATE; }
+    WaveEndGuard guard{ctx};
     CK(cudaSetDevice(ctx->cfg.device));
     const uint32_t n = ctx->waveN;
     if (n) {
@@ -698,6 +712,7 @@ pgi_status pgi_wait_wave_device(pgi_ctx *ctx, void *verdicts_device)
 {
     if (!ctx) return PGI_ERR_INVALID;
     if (!ctx->inFlight) { ctx->err = "no wave in flight"; return PGI_ERR_STATE; }
+    WaveEndGuard guard{ctx};
     CK(cudaSetDevice(ctx->cfg.device));
     const uint32_t n = ctx->waveN;
     if (n) {

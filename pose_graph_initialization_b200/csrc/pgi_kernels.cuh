@@ -259,14 +259,29 @@ __global__ void __launch_bounds__(kCtaThreads, 3) k1_score_hypotheses(WaveArgs a
 // ---------------------------------------------------------------------------------------------
 // K1, streaming form (the default on full waves): persistent CTAs, the correspondences travel HBM -> shared memory as
 // 1-D bulk async copies (cp.async.bulk, the TMA engine without a tensor map: a pair's rows are one contiguous run of 32 B
-// records) through a ring of kK1Stages x kK1TileRows-row tiles armed on mbarriers, so kK1Stages - 1 tiles (96 KB) are in
+// records) through a ring of kK1Stages x kK1TileRows-row tiles armed on mbarriers, so kK1Stages - 1 tiles (128 KB) are in
 // flight per SM while the warps score the tile that has landed.  Same arithmetic, same ballots, same per-slot
 // bookkeeping as k1_score_hypotheses; waves that ask for byte masks keep the direct-load kernel.
 // ---------------------------------------------------------------------------------------------
-constexpr int kK1Stages = 4;
-constexpr int kK1TileRows = 1024;  // 32 KB per stage
-constexpr int kK1TmaThreads = 1024; // one row of the tile per thread: 32 warps keep the FP64 pipe fed (scoring a row is ~45 non-fused
-                                    // FP64 operations: at the HBM rate of 32 B per row that is about half the FP64 issue rate)
+// Tile shape.  The first version scored one row per thread and tile (1 024 threads, 1 024-row tiles): ncu counted 237
+// thread instructions per scored row, three quarters of them the per-tile bookkeeping (barrier, cursor, ballots) — the
+// kernel was issue-bound at 0.34 of the HBM rate.  A tile now holds a whole 2 000-row pair (64 KB) and every thread
+// scores kK1RowsPerThread rows of it, so the bookkeeping is paid once per 4 rows and the rows give the FP64 pipe
+// independent work.
+#ifndef PGI_K1_TILE_ROWS
+#define PGI_K1_TILE_ROWS 2048
+#endif
+#ifndef PGI_K1_THREADS
+#define PGI_K1_THREADS 512
+#endif
+#ifndef PGI_K1_STAGES
+#define PGI_K1_STAGES 3
+#endif
+constexpr int kK1Stages = PGI_K1_STAGES;
+constexpr int kK1TileRows = PGI_K1_TILE_ROWS;   // 64 KB per stage
+constexpr int kK1TmaThreads = PGI_K1_THREADS;
+constexpr int kK1RowsPerThread = kK1TileRows / kK1TmaThreads;
+static_assert(kK1TileRows % kK1TmaThreads == 0 && kK1TmaThreads % 32 == 0, "tile rows must be a multiple of the CTA size");
 
 __device__ __forceinline__ uint32_t smemAddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbarInit(uint64_t *bar, uint32_t count)
@@ -300,7 +315,7 @@ __device__ __forceinline__ void bulkLoad(void *dstSmem, const void *srcGlobal, u
 // range, threshold, E of the first hypothesis) are fetched kK1MetaSlots at a time by as many threads in parallel and kept
 // in shared memory, so the streaming loop below never waits on a chain of dependent global loads (pair id -> offsets ->
 // threshold / hypothesis) between two tiles.
-constexpr int kK1MetaSlots = 256;
+constexpr int kK1MetaSlots = 128;
 struct K1Meta {
     uint64_t r0[kK1MetaSlots];
     double thr[kK1MetaSlots];
@@ -417,7 +432,9 @@ __global__ void __launch_bounds__(kK1TmaThreads, 1) k1_score_hypotheses_tma(Wave
             if (rows) {
                 const double4 *tile = tiles + (size_t)st * kK1TileRows;
                 uint32_t *bits = a.bits + ((size_t)w * 2 + (1u - sValidSel)) * a.bitsStride;
-                const uint32_t li = threadIdx.x;  // one row of the tile per thread
+#pragma unroll
+                for (int rr = 0; rr < kK1RowsPerThread; rr++) {
+                const uint32_t li = threadIdx.x + (uint32_t)rr * kK1TmaThreads;  // rows li of the tile: one 32-row group per warp and rr
                 if ((li & ~31u) < rows) {          // warp-uniform: the warp's 32-row group starts inside the tile
                     bool t = false, in = false;
                     if (li < rows) {
@@ -451,6 +468,7 @@ __global__ void __launch_bounds__(kK1TmaThreads, 1) k1_score_hypotheses_tma(Wave
                         cInl += __popc(bi);
                         bits[(cons.row0 + li) >> 5] = bi;
                     }
+                }
                 }
             }
             const bool hypEnd = haveHyp && cons.row0 + kK1TileRows >= N;
