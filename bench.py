@@ -326,12 +326,26 @@ def main():
     scene = make_scene(args.config)  # same seed on every rank => identical scene
     if args.wave <= 0:
         args.wave = B.default_wave_size(len(scene["focal"]), world, args.device_search)
-    # the step's host inputs live in PINNED memory (every step copies them host->device)
-    for key in ("matches", "kp", "sim", "pair_views", "m_offset", "kp_offset", "focal", "size"):
-        src = np.ascontiguousarray(scene[key])
-        pinned = torch.empty(src.nbytes, dtype=torch.uint8, pin_memory=True).numpy().view(src.dtype).reshape(src.shape)
-        pinned[...] = src
-        scene[key] = pinned
+    # the step's host inputs live in PINNED memory (every step copies them host->device).  With several ranks only the
+    # rank's own shard of the matches is registered, so only the shard is pinned (the full 8 GB list of the 1 000-view
+    # scene stays pageable, and only rank 0 keeps it: its CPU legs replay pairs of the whole scene)
+    def pin(d, keys):
+        for key in keys:
+            src = np.ascontiguousarray(d[key])
+            pinned = torch.empty(src.nbytes, dtype=torch.uint8, pin_memory=True).numpy().view(src.dtype).reshape(src.shape)
+            pinned[...] = src
+            d[key] = pinned
+
+    small = ("kp", "sim", "pair_views", "m_offset", "kp_offset", "focal", "size")
+    shard = None
+    if world == 1:
+        pin(scene, ("matches",) + small)
+    else:
+        pin(scene, small)
+        shard = B.shard_scene(scene, rank, world)
+        pin(shard, ("matches", "pair_views", "m_offset"))
+        if rank != 0:
+            scene["matches"] = np.zeros((0, 2), dtype=np.uint32)
     P = len(scene["pair_views"])
     n_corr = int(scene["m_offset"][1] - scene["m_offset"][0])
     pgb = B.PoseGraphBuilder(kCoreNumber_=max(1, (os.cpu_count() or 1) // world),  # ranks share the box's cores
@@ -339,6 +353,8 @@ def main():
                              prefetch_fallback=not args.lazy, overlap_fallback=not args.no_overlap, research_window=args.window,
                              fallback_wave=args.fb_wave, prefetch_streams=args.fb_streams, gpu_search=args.device_search,
                              gpu_search_min_batch=args.search_min_batch, group=group, rank=rank, world_size=world)
+    if shard is not None:
+        pgb._sub = shard
     pgb.prepare()
     fp64_peak = pgb.engine.fp64_peak(fused=False)
     fp64_peak_fma = pgb.engine.fp64_peak(fused=True)

@@ -220,6 +220,14 @@ pgi_status pgi_guided_match(pgi_ctx *ctx, uint32_t n_src, const float *kp_src, c
                             int32_t bin_number, uint32_t *matches_out, double *ratios_out, uint32_t *n_out,
                             double *prepared_or_null);
 
+/* ---- brute-force descriptor matching (K8) ------------------------------------------------------------------
+ * matchFeatures (feature_utils.h:103-210) without its HDF5 cache: BRUTEFORCE_SL2 2-NN in both directions, ratio test
+ * best/second < 0.90 on the squared distances, mutual nearest neighbour, survivors sorted by the ratio.
+ * desc_*: n x dim float descriptors (dim 128 or 64).  matches_out (capacity n_src x 2: queryIdx, trainIdx) and ratios_out
+ * (capacity n_src) receive the rows the reference appends to `matches_` (:196-204), *n_out their number. */
+pgi_status pgi_match_features(pgi_ctx *ctx, uint32_t n_src, const float *desc_src, uint32_t n_dst, const float *desc_dst,
+                              uint32_t dim, uint32_t *matches_out, double *ratios_out, uint32_t *n_out);
+
 pgi_status pgi_get_stats(pgi_ctx *ctx, pgi_stats *out);
 pgi_status pgi_reset_stats(pgi_ctx *ctx);
 

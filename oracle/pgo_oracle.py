@@ -387,3 +387,48 @@ def guided_match(kp_src, desc_src, kp_dst, desc_dst, pose_qt, K_src, K_dst, size
     n = int(n)
     k = int(nsel.value)
     return dict(matches=m[:n].copy(), ratios=r[:n].copy(), selected_matches=sm[:k].copy(), selected_ratios=sr[:k].copy(), prepared=prep[:14].copy())
+
+
+def match_features(desc_src, desc_dst):
+    """matchFeatures (feature_utils.h:103-210) restated with numpy: BRUTEFORCE_SL2 2-NN in both directions (:151-163), the
+    0.90 ratio test on the squared distances and the mutual-nearest-neighbour check (:172-184), survivors sorted by the
+    ratio (:188) -> (matches [n, 2] (queryIdx, trainIdx), ratios [n]).
+    The squared distance is accumulated in float32 in dimension order, multiply then add, and the 2-NN scan keeps the
+    first of equal distances first (cv::batchDistance's insertion rule) — OpenCV's own SIMD accumulation order depends
+    on the build, so its distances agree to ~1e-6 only (tests/test_oracle_features.py pins that against the cv2 wheel)."""
+    a = np.ascontiguousarray(desc_src, dtype=np.float32)
+    b = np.ascontiguousarray(desc_dst, dtype=np.float32)
+
+    def knn2(q, t):
+        nq, nt = len(q), len(t)
+        d1 = np.full(nq, np.finfo(np.float32).max, dtype=np.float32)
+        d2 = d1.copy()
+        i1 = np.full(nq, -1, dtype=np.int64)
+        if nq == 0 or nt == 0:
+            return d1, d2, i1
+        step = max(1, (1 << 22) // max(nq, 1))
+        for t0 in range(0, nt, step):
+            tt = t[t0:t0 + step]
+            acc = np.zeros((nq, len(tt)), dtype=np.float32)
+            for k in range(q.shape[1]):
+                d = q[:, k:k + 1] - tt[None, :, k]
+                acc = acc + d * d  # float32 multiply, then float32 add
+            for j in range(len(tt)):  # ascending train index, strict comparisons
+                c = acc[:, j]
+                better = c < d1
+                second = ~better & (c < d2)
+                d2 = np.where(better, d1, np.where(second, c, d2))
+                i1 = np.where(better, t0 + j, i1)
+                d1 = np.where(better, c, d1)
+        return d1, d2, i1
+
+    f1, f2, fi = knn2(a, b)
+    g1, g2, gi = knn2(b, a)
+    out = []
+    if len(b) >= 2 and len(a) >= 2:  # matches[i].size() < 2 || matches_opposite[...].size() < 2 -> continue  (:174-176)
+        for i in range(len(a)):
+            if float(f1[i]) < 0.90 * float(f2[i]) and gi[fi[i]] == i:  # (:178-179) float < double * float
+                out.append((float(np.float32(f1[i]) / np.float32(f2[i])), i, int(fi[i])))
+    out.sort(key=lambda r: (r[0], r[1]))  # std::sort on (ratio, &matches[i])  (:188)
+    m = np.array([(i, j) for _, i, j in out], dtype=np.uint32).reshape(-1, 2)
+    return m, np.array([r for r, _, _ in out], dtype=np.float64)

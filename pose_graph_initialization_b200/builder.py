@@ -460,7 +460,13 @@ class PoseGraphBuilder:
     def prepare(self):
         if self.engine is None:
             self.engine = _engine.Engine(device=self.device, min_inliers=self.min_inliers)
-        sub = self.scene if self.world == 1 else shard_scene(self.scene, self.rank, self.world)
+        if self.world == 1:
+            sub = self.scene
+        else:
+            # the rank's shard is cut once (a 32 GB scene's shard is gigabytes: not something to copy on every registration)
+            if getattr(self, "_sub", None) is None:
+                self._sub = shard_scene(self.scene, self.rank, self.world)
+            sub = self._sub
         self.engine.register_scene(sub, self.thr_px)
         self.prepared = True
         if self.overlap:

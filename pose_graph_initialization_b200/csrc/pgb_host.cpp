@@ -40,6 +40,7 @@
 #include <vector>
 
 #include "../../include/pgb.h"
+#include "pgi_nvtx.h"
 
 #if defined(__x86_64__) && defined(__GNUC__)
 #include <immintrin.h>
@@ -857,6 +858,7 @@ inline bool isDuplicate(const pgb_builder *b, const Item &it)
 }
 void rebuildOverlay(pgb_builder *b, uint32_t from = 0)
 {
+    PgiNvtxRange nvtxRange("pgb:rebuild overlay + simulated visibility");
     const double t0 = nowSec();
     b->ovDirty = true;
     bool allLinked = true;
@@ -1098,6 +1100,7 @@ void checkDeviceSearches(pgb_builder *b)
 // first stale position; unlimited by default).
 void searchStale(pgb_builder *b, uint32_t limit)
 {
+    PgiNvtxRange nvtxRange("pgb:A* round (stale positions, thread pool)");
     const double t0 = nowSec();
     std::vector<uint32_t> todo;
     for (uint32_t k = 0; k < b->wave.size() && k < limit; k++)
@@ -1355,6 +1358,7 @@ uint32_t advanceWave(pgb_builder *b)
         rebuildOverlay(b, firstChanged);
     }
     const double t0 = nowSec();
+    PgiNvtxRange nvtxCommit("pgb:commit wave in order");
     b->commitEntries.clear();
     for (Item &it : b->wave) commitPosition(b, it);
     b->wave.clear();
@@ -1586,6 +1590,7 @@ void pgb_copy_sim_table(pgb_builder *b, double *out) { memcpy(out, b->sim.data()
 int32_t pgb_run_wave(pgb_builder *b, uint32_t wave_size, pgb_submit_fn submit, pgb_wait_fn wait, void *engine, uint32_t flags,
                      pgb_drive_stats *stats)
 {
+    PgiNvtxRange nvtxRange("pgb:run_wave");
     if (!b || !submit || !wait || wave_size == 0) return -1;
     double t0 = nowSec();
     uint32_t n;

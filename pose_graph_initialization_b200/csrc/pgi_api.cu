@@ -16,6 +16,8 @@
 #include "pgi_kernels.cuh"
 #include "pgi_astar.cuh"
 #include "pgi_matcher.cuh"
+#include "pgi_features.cuh"
+#include "pgi_nvtx.h"
 
 using namespace pgi;
 
@@ -572,6 +574,7 @@ const char *pgi_last_error(pgi_ctx *ctx) { return ctx ? ctx->err.c_str() : "null
 pgi_status pgi_register_pairs(pgi_ctx *ctx, uint64_t n_pairs, const uint64_t *corr_offset, const double *corr_xy4,
                               const double *thr_norm)
 {
+    PgiNvtxRange nvtxRange("pgi:register_pairs");
     if (!ctx) return PGI_ERR_INVALID;
     if (ctx->inFlight) { ctx->err = "a wave is in flight"; return PGI_ERR_STATE; }
     CK(cudaSetDevice(ctx->cfg.device));
@@ -584,6 +587,7 @@ pgi_status pgi_register_scene(pgi_ctx *ctx, uint64_t n_views, const double *foca
                               const uint32_t *pair_views, const uint64_t *m_offset, const uint32_t *matches,
                               double thr_px)
 {
+    PgiNvtxRange nvtxRange("pgi:register_scene (H2D + K0)");
     if (!ctx) return PGI_ERR_INVALID;
     if (ctx->inFlight) { ctx->err = "a wave is in flight"; return PGI_ERR_STATE; }
     if (!focal || !size_wh || !kp_offset || !kp_xy || !pair_views || !m_offset || (!matches && m_offset[n_pairs])) {
@@ -683,6 +687,7 @@ pgi_status pgi_read_pair(pgi_ctx *ctx, uint32_t pair_id, double *corr_xy4, uint6
 pgi_status pgi_submit_wave(pgi_ctx *ctx, uint32_t n, const uint32_t *pair_id, const uint32_t *hyp_offset,
                            const double *hyp_q_t, uint32_t flags)
 {
+    PgiNvtxRange nvtxRange("pgi:submit_wave (H2D hypotheses + K1/K2/K4/K5/K3 launches)");
     if (!ctx) return PGI_ERR_INVALID;
     CK(cudaSetDevice(ctx->cfg.device));
     return submitWave(ctx, ctx->reg, n, pair_id, hyp_offset, hyp_q_t, flags, 0.0, 0, false);
@@ -690,6 +695,7 @@ pgi_status pgi_submit_wave(pgi_ctx *ctx, uint32_t n, const uint32_t *pair_id, co
 
 pgi_status pgi_wait_wave(pgi_ctx *ctx, pgi_verdict *out, uint8_t *masks_or_null)
 {
+    PgiNvtxRange nvtxRange("pgi:wait_wave (sync + D2H verdicts)");
     if (!ctx) return PGI_ERR_INVALID;
     if (!ctx->inFlight) { ctx->err = "no wave in flight"; return PGI_ERR_STATE; }
     WaveEndGuard guard{ctx};
@@ -710,6 +716,7 @@ pgi_status pgi_wait_wave(pgi_ctx *ctx, pgi_verdict *out, uint8_t *masks_or_null)
 
 pgi_status pgi_wait_wave_device(pgi_ctx *ctx, void *verdicts_device)
 {
+    PgiNvtxRange nvtxRange("pgi:wait_wave_device");
     if (!ctx) return PGI_ERR_INVALID;
     if (!ctx->inFlight) { ctx->err = "no wave in flight"; return PGI_ERR_STATE; }
     WaveEndGuard guard{ctx};
@@ -873,6 +880,7 @@ pgi_status pgi_graph_apply(pgi_ctx *ctx, uint32_t n_entries, const pgi_adj_entry
 pgi_status pgi_graph_search(pgi_ctx *ctx, uint32_t n, const pgi_query *queries, uint32_t max_depth, double weight,
                             pgi_search_result *results, uint32_t *expanded_bits)
 {
+    PgiNvtxRange nvtxRange("pgi:graph_search (K6)");
     if (!ctx) return PGI_ERR_INVALID;
     if (!ctx->d_adj) { ctx->err = "pgi_graph_init has not been called"; return PGI_ERR_STATE; }
     if (n == 0) return PGI_OK;
@@ -954,6 +962,7 @@ pgi_status pgi_guided_match(pgi_ctx *ctx, uint32_t n_src, const float *kp_src, c
                             int32_t bin_number, uint32_t *matches_out, double *ratios_out, uint32_t *n_out,
                             double *prepared_or_null)
 {
+    PgiNvtxRange nvtxRange("pgi:guided_match (K7)");
     if (!ctx) return PGI_ERR_INVALID;
     if (!pose_q_t || !K_src || !K_dst || !size_src || !size_dst || !n_out || (n_src && (!kp_src || !desc_src || !matches_out || !ratios_out)) ||
         (n_dst && (!kp_dst || !desc_dst)) || dim == 0 || bin_number > kMatchMaxBins) {
@@ -1022,6 +1031,69 @@ pgi_status pgi_guided_match(pgi_ctx *ctx, uint32_t n_src, const float *kp_src, c
     return PGI_OK;
 }
 
+pgi_status pgi_match_features(pgi_ctx *ctx, uint32_t n_src, const float *desc_src, uint32_t n_dst, const float *desc_dst,
+                              uint32_t dim, uint32_t *matches_out, double *ratios_out, uint32_t *n_out)
+{
+    PgiNvtxRange nvtxRange("pgi:match_features (K8)");
+    if (!ctx) return PGI_ERR_INVALID;
+    if (!n_out || (n_src && (!desc_src || !matches_out || !ratios_out)) || (n_dst && !desc_dst) || (dim != 128 && dim != 64)) {
+        ctx->err = "bad argument (descriptors must have 64 or 128 dimensions)";
+        return PGI_ERR_INVALID;
+    }
+    CK(cudaSetDevice(ctx->cfg.device));
+    *n_out = 0;
+    if (n_src == 0 || n_dst == 0) return PGI_OK;
+    cudaStream_t s = ctx->stream;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t bS = n_src, bD = n_dst;
+    const size_t oA = 0, oB = oA + al(bS * dim * 4), oF = oB + al(bD * dim * 4), oG = oF + al(bS * sizeof(Knn2)),
+                 oM = oG + al(bD * sizeof(Knn2)), oR = oM + al(bS * 8), oN = oR + al(bS * 8), total = oN + 256;
+    unsigned char *d = nullptr;
+    CK(cudaMalloc((void **)&d, total));
+    auto fail = [&](cudaError_t e) { cudaFree(d); ctx->err = cudaGetErrorString(e); return PGI_ERR_CUDA; };
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(d + oA, desc_src, bS * dim * 4, cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(e);
+    if ((e = cudaMemcpyAsync(d + oB, desc_dst, bD * dim * 4, cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(e);
+    const float *A = reinterpret_cast<const float *>(d + oA), *B = reinterpret_cast<const float *>(d + oB);
+    Knn2 *F = reinterpret_cast<Knn2 *>(d + oF), *G = reinterpret_cast<Knn2 *>(d + oG);
+    if (dim == 128) {
+        k8_knn2<128><<<(n_src + kFeatThreads - 1) / kFeatThreads, kFeatThreads, 0, s>>>(A, n_src, B, n_dst, F);  // feature_utils.h:158-159
+        k8_knn2<128><<<(n_dst + kFeatThreads - 1) / kFeatThreads, kFeatThreads, 0, s>>>(B, n_dst, A, n_src, G);  // :162-163
+    } else {
+        k8_knn2<64><<<(n_src + kFeatThreads - 1) / kFeatThreads, kFeatThreads, 0, s>>>(A, n_src, B, n_dst, F);
+        k8_knn2<64><<<(n_dst + kFeatThreads - 1) / kFeatThreads, kFeatThreads, 0, s>>>(B, n_dst, A, n_src, G);
+    }
+    k8_mutual<<<1, 1024, 0, s>>>(F, n_src, G, n_dst, reinterpret_cast<uint32_t *>(d + oM), reinterpret_cast<double *>(d + oR),
+                                 reinterpret_cast<uint32_t *>(d + oN));
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail(e);
+    uint32_t n = 0;
+    if ((e = cudaMemcpyAsync(&n, d + oN, 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return fail(e);
+    if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return fail(e);
+    if (n > n_src) n = n_src;
+    std::vector<uint32_t> m((size_t)2 * n);
+    std::vector<double> r(n);
+    if (n) {
+        if ((e = cudaMemcpy(m.data(), d + oM, (size_t)n * 8, cudaMemcpyDeviceToHost)) != cudaSuccess) return fail(e);
+        if ((e = cudaMemcpy(r.data(), d + oR, (size_t)n * 8, cudaMemcpyDeviceToHost)) != cudaSuccess) return fail(e);
+    }
+    cudaFree(d);
+    // std::sort of (ratio, &matches[i]) pairs (feature_utils.h:188): by ratio, then by the address of the query's
+    // match vector, i.e. by query index
+    std::vector<uint32_t> order(n);
+    for (uint32_t i = 0; i < n; i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return r[x] != r[y] ? r[x] < r[y] : m[2 * x] < m[2 * y]; });
+    for (uint32_t i = 0; i < n; i++) {
+        matches_out[2 * i] = m[2 * order[i]];
+        matches_out[2 * i + 1] = m[2 * order[i] + 1];
+        ratios_out[i] = r[order[i]];
+    }
+    *n_out = n;
+    ctx->stats.launches += 3;
+    ctx->stats.h2d_bytes += (bS + bD) * dim * 4;
+    ctx->stats.d2h_bytes += (size_t)n * 16 + 4;
+    return PGI_OK;
+}
+
 pgi_status pgi_get_stats(pgi_ctx *ctx, pgi_stats *out)
 {
     if (!ctx || !out) return PGI_ERR_INVALID;
@@ -1054,9 +1126,9 @@ __global__ void kdbg_five_point(const double *x1, const double *x2, uint32_t n, 
     if (i >= n) return;
     double a[10], b[10];
     for (int k = 0; k < 10; k++) { a[k] = x1[10 * (size_t)i + k]; b[k] = x2[10 * (size_t)i + k]; }
-    // the legacy (tolerance 0) mode exercises the exact cycle jump used by K2
-    count[i] = dkTolSq == 0.0 ? fivePoint<true>(a, b, Eout + 90 * (size_t)i, 10, dkMaxIters, dkTolSq)
-                              : fivePoint<false>(a, b, Eout + 90 * (size_t)i, 10, dkMaxIters, dkTolSq);
+    // 1000 sweeps (with or without a tolerance) = K2's configuration: the exact cycle jump; fewer sweeps = K4's plain loop
+    count[i] = dkMaxIters >= 1000 ? fivePoint<true>(a, b, Eout + 90 * (size_t)i, 10, dkMaxIters, dkTolSq)
+                                  : fivePoint<false>(a, b, Eout + 90 * (size_t)i, 10, dkMaxIters, dkTolSq);
 }
 }  // namespace
 

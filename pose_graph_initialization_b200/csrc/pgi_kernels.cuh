@@ -534,7 +534,10 @@ __device__ inline uint32_t selectRank(const uint32_t *bits, uint32_t nWords, uin
 // MWC RNG(2^64-1) draws 5 distinct ranks in [0,k); the first solution of the first sample that yields
 // a model wins and every point is its inlier.  One thread per wave pair (a warp of its own on
 // small waves, where the kernel is a latency chain).  The Durand-Kerner
-// root solve stops at convergence (kLegacyDkTolSq) rather than burning cv::solvePoly's 1000 fixed sweeps — same
+// root solve stops at convergence (kLegacyDkTolSq) rather than burning cv::solvePoly's 1000 fixed sweeps, and the ~2 % of
+// polynomials whose sweeps fall into a floating-point cycle without ever reaching the tolerance jump to the state sweep
+// 1000 would produce (Brent's cycle detection on the bitwise root state, dkSolveFixed<., true>: identical to running
+// every sweep) — before, one such straggler per wave round held the whole engine round trip for ~1.3 ms — same
 // trajectory, same root order, values equal to cv2's to ~1e-13 (the oracle does the same and is pinned to cv2).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(64) k2_fivept_first_solution(WaveArgs a, int onePairPerWarp)
@@ -565,8 +568,8 @@ __global__ void __launch_bounds__(64) k2_fivept_first_solution(WaveArgs a, int o
                 const double4 c = rows[selectRank(bits, nWords, i)];
                 x1[2 * i] = c.x; x1[2 * i + 1] = c.y; x2[2 * i] = c.z; x2[2 * i + 1] = c.w;
             }
-            found = (onePairPerWarp ? fivePoint<false, true>(x1, x2, E, 1, 1000, kLegacyDkTolSq, sWs)
-                                    : fivePoint<false>(x1, x2, E, 1, 1000, kLegacyDkTolSq)) > 0;
+            found = (onePairPerWarp ? fivePoint<true, true>(x1, x2, E, 1, 1000, kLegacyDkTolSq, sWs)
+                                    : fivePoint<true>(x1, x2, E, 1, 1000, kLegacyDkTolSq)) > 0;
         } else {
             CvRng rng((uint64_t)-1);
             for (int iter = 0; iter < 1000 && !found; iter++) {
@@ -584,8 +587,8 @@ __global__ void __launch_bounds__(64) k2_fivept_first_solution(WaveArgs a, int o
                     x1[2 * i] = c.x; x1[2 * i + 1] = c.y; x2[2 * i] = c.z; x2[2 * i + 1] = c.w;
                 }
                 // the RANSAC loop keeps the first solution that has inliers at all, i.e. the first finite one
-                found = (onePairPerWarp ? fivePoint<false, true>(x1, x2, E, 1, 1000, kLegacyDkTolSq, sWs, true)
-                                        : fivePoint<false>(x1, x2, E, 1, 1000, kLegacyDkTolSq, nullptr, true)) > 0;
+                found = (onePairPerWarp ? fivePoint<true, true>(x1, x2, E, 1, 1000, kLegacyDkTolSq, sWs, true)
+                                        : fivePoint<true>(x1, x2, E, 1, 1000, kLegacyDkTolSq, nullptr, true)) > 0;
             }
         }
         if (!(flags & ST_NEED_5PT)) {

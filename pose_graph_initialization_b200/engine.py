@@ -46,7 +46,7 @@ EXPORTS = [
     "pgi_version", "pgi_device_count", "pgi_create", "pgi_destroy", "pgi_last_error", "pgi_register_pairs",
     "pgi_register_scene", "pgi_share_pairs", "pgi_read_pair", "pgi_submit_wave", "pgi_wait_wave", "pgi_wait_wave_device",
     "pgi_estimate_pose", "pgi_test_pose", "pgi_graph_init", "pgi_graph_apply", "pgi_graph_search", "pgi_graph_stats",
-    "pgi_guided_match", "pgi_get_stats", "pgi_reset_stats", "pgi_dbg_sampson",
+    "pgi_guided_match", "pgi_match_features", "pgi_get_stats", "pgi_reset_stats", "pgi_dbg_sampson",
     "pgi_dbg_five_point", "pgi_dbg_pose_from_essential", "pgi_dbg_fp64_peak",
 ]
 
@@ -285,6 +285,21 @@ class Engine:
         else:
             selected = [(int(a), int(b), float(ratios[0])) for a, b in matches]
         return dict(matches=matches, ratios=ratios, selected=selected, prepared=prep)
+
+    def match_features(self, desc_src, desc_dst):
+        """matchFeatures (feature_utils.h:103-210) on the device: -> (matches [n, 2] (queryIdx, trainIdx), ratios [n]),
+        sorted by ratio as the reference stores them."""
+        ds = np.ascontiguousarray(desc_src, dtype=np.float32)
+        dd = np.ascontiguousarray(desc_dst, dtype=np.float32)
+        if ds.ndim != 2 or dd.ndim != 2 or ds.shape[1] != dd.shape[1] or ds.shape[1] not in (64, 128):
+            raise ValueError("descriptors must be [n, 64] or [n, 128] float arrays of equal width")
+        m = np.zeros((max(len(ds), 1), 2), dtype=np.uint32)
+        r = np.zeros(max(len(ds), 1))
+        n = C.c_uint32(0)
+        self._ck(self.lib.pgi_match_features(self.h, C.c_uint32(len(ds)), _ptr(ds), C.c_uint32(len(dd)), _ptr(dd),
+                                             C.c_uint32(ds.shape[1]), _ptr(m), _ptr(r), C.byref(n)))
+        k = int(n.value)
+        return m[:k].copy(), r[:k].copy()
 
     # ---- stats / debug -------------------------------------------------------------------------------------
     def stats(self):

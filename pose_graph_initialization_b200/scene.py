@@ -176,3 +176,47 @@ def load_scene(path):
         return dict(focal=rd("<f8", (V,)), size=rd("<f8", (V, 2)), sim=rd("<f8", (V, V)),
                     kp_offset=rd("<u8", (V + 1,)), kp=rd("<f4", (K, 2)), pair_views=rd("<u4", (P, 2)),
                     m_offset=rd("<u8", (P + 1,)), matches=rd("<u4", (M, 2)))
+
+
+# ---- the reference's two plain-text inputs (the HDF5 caches cannot be read here: no HDF5 in this image) ------------------
+def load_1dsfm_image_list(path):
+    """load1DSfMImageList (utils.h:120-182) without the image-size pass: every line of `list_with_focals.txt` is
+    `images/<name> <flag> <focal>`; the name drops its first 7 characters (utils.h:149), the third token is the focal
+    length (std::atof, :154).  A line without a third token keeps an indeterminate focal length in the reference; it is
+    reported as 0.0 here.  Returns (names, focal[V])."""
+    names, focal = [], []
+    with open(path) as f:
+        for line in f:  # the reference counts and keeps every line, also empty ones (:137-170)
+            tok = line.split()
+            names.append(tok[0][7:] if tok else "")
+            try:
+                focal.append(float(tok[2]) if len(tok) > 2 else 0.0)
+            except ValueError:
+                focal.append(0.0)  # std::atof of a non-number
+    return names, np.asarray(focal, dtype=np.float64)
+
+
+def load_similarity_matrix(path, n_views):
+    """SimilarityTable::loadFromFile (imagesimilarity_graph.h:108-171): one whitespace-separated row per line; the file must
+    have exactly n_views rows of n_views values (the reference logs and returns false otherwise: ValueError here).  The
+    similarity-ordered pair queue the reference builds while reading (:141-157) is built by pgb_create from the returned
+    matrix.  Returns sim[V, V] float64."""
+    rows = []
+    with open(path) as f:
+        for line in f:
+            vals = []
+            for tok in line.split():
+                try:
+                    vals.append(float(tok))
+                except ValueError:
+                    break  # `ss >> value` stops at the first token that is not a number
+            rows.append(vals)
+    if len(rows) != n_views or any(len(r) != n_views for r in rows):
+        raise ValueError("%s has different size than the initialised similarity map (%d views)" % (path, n_views))
+    return np.asarray(rows, dtype=np.float64)
+
+
+def save_similarity_matrix(path, sim):
+    with open(path, "w") as f:
+        for row in np.asarray(sim):
+            f.write(" ".join(repr(float(x)) for x in row) + "\n")

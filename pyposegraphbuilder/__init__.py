@@ -8,13 +8,15 @@ ValueError on shape errors.
     pose, inliers = ppg.estimate_pose(corr, thr_norm, poses=[q_t])      # PoseGraphBuilder::estimatePose  PGB:940-1078
     ok, count = ppg.test_pose(corr, thr, pose)                          # InTraversalPoseTester::test    GT:194-233
     matches, ratios = ppg.guided_match(kp1, desc1, kp2, desc2, pose, K1, K2, size1, size2)   # matcher.h:199-405
+    matches, ratios = ppg.match_features(desc1, desc2)                   # matchFeatures                  feature_utils.h:103-210
+    tracks = ppg.Tracklets(n_views); tracks.add(i, j, matches, mask)    # reconstruction::Tracklets      point_track.h:541-712
     graph = ppg.PoseGraphBuilder(**flags, scene=scene).run()            # PoseGraphBuilder::run           PGB:173-239
 
 Everything runs on the sm_100a engine through the C-ABI (include/pgi.h, include/pgb.h); there is no CPU path."""
 import numpy as np
 
 from pose_graph_initialization_b200 import Engine  # noqa: F401
-from pose_graph_initialization_b200.builder import PoseGraphBuilder  # noqa: F401
+from pose_graph_initialization_b200.builder import PoseGraphBuilder, Tracklets  # noqa: F401
 from pose_graph_initialization_b200 import scene  # noqa: F401
 
 _engine = None
@@ -54,3 +56,8 @@ def guided_match(kp_src, desc_src, kp_dst, desc_dst, pose, K_src, K_dst, size_sr
     """-> (matches [(src, dst, value)] as guidedMatching returns them, all matches [n, 2], adapted ratios [n])."""
     r = _eng().guided_match(kp_src, desc_src, kp_dst, desc_dst, pose, K_src, K_dst, size_src, size_dst, 45, max_points)
     return r["selected"], r["matches"], r["ratios"]
+
+
+def match_features(desc_src, desc_dst):
+    """-> (matches [n, 2] (queryIdx, trainIdx), ratios [n]) as matchFeatures stores them (sorted by ratio)."""
+    return _eng().match_features(desc_src, desc_dst)
