@@ -534,10 +534,10 @@ __device__ inline uint32_t selectRank(const uint32_t *bits, uint32_t nWords, uin
 // MWC RNG(2^64-1) draws 5 distinct ranks in [0,k); the first solution of the first sample that yields
 // a model wins and every point is its inlier.  One thread per wave pair (a warp of its own on
 // small waves, where the kernel is a latency chain).  The Durand-Kerner
-// root solve stops at convergence (kLegacyDkTolSq) rather than burning cv::solvePoly's 1000 fixed sweeps, and the ~2 % of
-// polynomials whose sweeps fall into a floating-point cycle without ever reaching the tolerance jump to the state sweep
-// 1000 would produce (Brent's cycle detection on the bitwise root state, dkSolveFixed<., true>: identical to running
-// every sweep) — before, one such straggler per wave round held the whole engine round trip for ~1.3 ms — same
+// root solve stops at convergence (kLegacyDkTolSq) rather than burning cv::solvePoly's 1000 fixed sweeps; polynomials
+// whose sweeps fall into an exact floating-point cycle jump to the state sweep 1000 would produce (Brent's cycle
+// detection on the bitwise root state, dkSolveFixed<., true>: identical to running every sweep).  The few % that neither
+// converge nor cycle run all 1000 sweeps (3 us each) and set the latency of the wave round they are in — same
 // trajectory, same root order, values equal to cv2's to ~1e-13 (the oracle does the same and is pinned to cv2).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(64) k2_fivept_first_solution(WaveArgs a, int onePairPerWarp)
