@@ -435,7 +435,7 @@ class PoseGraphBuilder:
         self.group, self.rank, self.world = group, rank, world_size
         # overlap the hypothesis-independent fallback (second context, own low-priority stream, driven by a worker
         # thread) with the sequential waves; with several ranks the worker exchanges each chunk's verdicts over its own
-        # gloo group so that it never shares a communicator with the wave loop
+        # gloo group so that it never shares a communicator (or NCCL's ordering requirements) with the wave loop
         self.overlap = bool(overlap_fallback and prefetch_fallback)
         self.pf_group = None
         self.pf_device = None
@@ -479,14 +479,18 @@ class PoseGraphBuilder:
                     self.engine_fb2 = _engine.Engine(device=self.device, min_inliers=self.min_inliers, background=True)
                 self.engine_fb2.share_pairs(self.engine)
             if self.world > 1 and self.pf_group is None:
-                # the prefetch worker thread gathers its chunks' verdicts over its OWN communicator (never shared with the
-                # wave loop's): NCCL over NVLink on device buffers when the job runs on GPUs, gloo in the CPU tests
-                import torch
+                # The prefetch worker thread gathers its chunks' verdicts over its OWN communicator, and that communicator
+                # is gloo (CPU tensors, as in round 1) on purpose.  A second NCCL communicator driven from the worker thread
+                # was tried in round 2 and deadlocked on the 1 000-view scene at N=2 (all-gather #77 of the prefetch group
+                # against all-reduce #283 of the wave loop, both ranks in the watchdog after 600 s): two NCCL communicators
+                # used concurrently must enqueue their collectives in the same order on every rank, which two free-running
+                # threads do not, and on a GPU saturated by the fallback kernels the two collective kernels cannot
+                # co-schedule their way out of it.  (On the 300-view scene the same code happened to work.)  The payload is
+                # 330 KB per chunk; gloo moves it in about a millisecond.
                 import torch.distributed as dist
-                on_gpu = torch.cuda.is_available() and dist.get_backend() == "nccl"
-                self.pf_group = dist.new_group(backend="nccl" if on_gpu else "gloo")
-                self.pf_device = torch.device("cuda", self.device) if on_gpu else None
-                self.pf_stream = torch.cuda.Stream(device=self.pf_device) if on_gpu else None
+                self.pf_group = dist.new_group(backend="gloo")
+                self.pf_device = None
+                self.pf_stream = None
 
     def engine_stats(self):
         st = self.engine.stats()
