@@ -90,3 +90,87 @@ def test_interleaved_ownership():
 
     assert list(B.owner_of([0, 1, 2, 4, 5, 9], 4)) == [0, 1, 2, 0, 1, 1]
     assert list(B.local_id([0, 1, 2, 4, 5, 9], 4)) == [0, 0, 0, 1, 1, 2]
+
+
+def _dense_worker(rank, world, port, wave, ret):
+    sys.path.insert(0, ROOT); sys.path.insert(0, HERE)
+    import torch.distributed as dist
+
+    import fake_verdicts as F
+    from pose_graph_initialization_b200 import builder as B
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    F.FB_SCORE[:] = [0.29, 0.06]      # the benchmark scenes' score mix: path-branch edges score lower than the fallback
+    F.PATH_SCORE[:] = [0.06, 0.19]    # edges they replace, so most prediction changes fall under the fine staleness rule
+    sc = F.dense_scene(90, n_corr=2000, seed=6, ring_cameras=True)
+    cfg = dict(similarity_threshold=0.0, minimum_inlier_number=20, minimum_point_number=50, maximum_search_depth=5,
+               traversal_heuristics_weight=0.8, use_path_finding=True)
+    host = B.HostBuilder(sc, host_threads=2, lazy_fallback=False, **cfg)
+    all_items = np.zeros(host.n_pairs, dtype=B.ITEM_DTYPE)
+    all_items["pair_id"] = np.arange(host.n_pairs, dtype=np.uint32)
+    host.set_fallback_verdicts(F.fake_verdicts(all_items, 2000))
+    host.set_partition(rank, world)
+    exchanges = 0
+    while host.remaining() > 0:
+        items = host.next_wave(wave)
+        status = host.wave_status()
+        while status != B.WAVE_DONE:
+            if status == B.WAVE_NEED_GPU:
+                todo = items[items["need_gpu"] > 0]
+                assert np.all(B.owner_of(todo["pair_id"], world) == rank)
+                host.commit_wave(F.fake_verdicts(todo, 2000, fallback=False))
+            else:
+                host.import_records(B.allreduce_records(host.export_records()))
+                exchanges += 1
+            status = host.wave_status()
+            if status != B.WAVE_DONE:
+                items = host.next_wave(wave)
+    lg = host.log()
+    names = [n for n in lg.dtype.names if n != "touchedNodes"]  # a non-owner does not run the search of a position
+    c = host.counters()
+    ret[rank] = (lg[names].tobytes(), host.edges().tobytes(), exchanges, int(c["stale_spared"]), int(c["astar_runs"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_three_ranks_on_a_dense_graph_commit_what_one_rank_commits_sequentially():
+    """Dense ring-camera graph, fake verdicts with the benchmark's score mix, waves of 1 024 positions (the multi-rank
+    default) on three ranks: every rank's log and edge list must be byte-identical to a single rank running wave = 1 (the
+    sequential semantics).  Exercises rank-sharded searches, the record all-reduce, the cost floor and the fine
+    staleness rule together at a density the 9-view oracle-backed test cannot reach."""
+    sys.path.insert(0, HERE)
+    import fake_verdicts as F
+    from pose_graph_initialization_b200 import builder as B
+
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = 31500 + (os.getpid() % 2000)
+    world = 3
+    procs = [ctx.Process(target=_dense_worker, args=(r, world, port, 1024, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=900)
+        assert p.exitcode == 0
+    # the sequential run, in this process
+    fb, ps = list(F.FB_SCORE), list(F.PATH_SCORE)
+    try:
+        F.FB_SCORE[:] = [0.29, 0.06]
+        F.PATH_SCORE[:] = [0.06, 0.19]
+        sc = F.dense_scene(90, n_corr=2000, seed=6, ring_cameras=True)
+        cfg = dict(similarity_threshold=0.0, minimum_inlier_number=20, minimum_point_number=50, maximum_search_depth=5,
+                   traversal_heuristics_weight=0.8, use_path_finding=True)
+        host = B.HostBuilder(sc, host_threads=1, lazy_fallback=False, **cfg)
+        F.drive(host, 1, 2000)
+        lg = host.log()
+        names = [n for n in lg.dtype.names if n != "touchedNodes"]
+        seq = (lg[names].tobytes(), host.edges().tobytes())
+        assert host.counters()["path_accepted"] > 500
+    finally:
+        F.FB_SCORE[:] = fb
+        F.PATH_SCORE[:] = ps
+    for r in range(world):
+        assert ret[r][0] == seq[0] and ret[r][1] == seq[1], r
+        assert ret[r][2] > 0
+    assert sum(ret[r][3] for r in range(world)) > 0  # results kept by the fine staleness rule
