@@ -278,6 +278,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--config", default="cfg3_1000v")
+    ap.add_argument("--step", default="batch", choices=("batch", "pass"),
+                    help="what one step is: 'batch' (default) = 1/K of the queue, the K timed steps together are ONE complete pass "
+                         "over the scene (the W warm-up steps are the first batches of an untimed pass run before); 'pass' = every "
+                         "step is a complete pass (K + W passes)")
     ap.add_argument("--wave", type=int, default=0, help="queue positions per speculative wave (0 = default of the config)")
     ap.add_argument("--window", type=int, default=0, help="host re-search window (0 = library default)")
     ap.add_argument("--no-overlap", action="store_true", help="prefetch the fallback before the waves instead of concurrently")
@@ -359,32 +363,54 @@ def main():
     fp64_peak = pgb.engine.fp64_peak(fused=False)
     fp64_peak_fma = pgb.engine.fp64_peak(fused=True)
 
-    for _ in range(args.warmup):
-        pgb.run()
+    K = max(args.steps, 1)
+    batch_steps = args.step == "batch"
+    batch = -(-P // K)  # queue positions per step in batch mode (cut at the next wave boundary)
+    if batch_steps:
+        # warm-up: one untimed pass driven exactly like the timed one; its first W batches are the warm-up steps
+        if args.warmup > 0:
+            for _ in pgb.run_in_batches(batch):
+                pass
+    else:
+        for _ in range(args.warmup):
+            pgb.run()
     pgb.reset_engine_stats()
     sampler = ClockSampler(local_rank)
-    K = max(args.steps, 1)
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
     step_wall = {"e2e": [], "detail": []}
     barrier()
     sampler.start()
     t0 = time.perf_counter()
     counters, timing, search_stats = None, None, None
+    gen, graph = None, None
     for k in range(K):
         ts = time.perf_counter()
         evs[k][0].record()
-        pgb.prepare()          # H2D of the compact scene from pinned host buffers + K0 (synchronous)
+        if not batch_steps or k == 0:
+            pgb.prepare()      # H2D of the compact scene from pinned host buffers + K0 (synchronous)
         barrier()
         evs[k][1].record()
         tp = time.perf_counter()
-        graph = pgb.run()      # inputs resident in HBM from here on
-        n_edges = graph.numEdges()
+        if not batch_steps:
+            graph = pgb.run()  # inputs resident in HBM from here on
+        else:
+            if k == 0:
+                gen = pgb.run_in_batches(batch)
+            if gen is not None:
+                try:
+                    next(gen)          # the next `batch` queue positions of the pass
+                    while k == K - 1:  # the last step ends with the pass, wherever the wave boundaries fell
+                        next(gen)
+                except StopIteration as done:
+                    graph, gen = done.value, None
         barrier()
         evs[k][2].record()
         step_wall["e2e"].append(round((time.perf_counter() - ts) * 1e3, 1))
-        step_wall["detail"].append({"prepare_ms": round((tp - ts) * 1e3, 1),
-                                    **{kk: round(v * 1e3, 1) for kk, v in pgb.timing.items() if kk.endswith("_s")}})
-        counters, timing, search_stats = pgb.counters, dict(pgb.timing), dict(getattr(pgb, "search_stats", {}) or {})
+        if not batch_steps or (graph is not None and counters is None):  # (batch steps: once, when the pass is complete)
+            step_wall["detail"].append({"prepare_ms": round((tp - ts) * 1e3, 1),
+                                        **{kk: round(v * 1e3, 1) for kk, v in pgb.timing.items() if kk.endswith("_s")}})
+            counters, timing, search_stats = pgb.counters, dict(pgb.timing), dict(getattr(pgb, "search_stats", {}) or {})
+    n_edges = graph.numEdges()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
@@ -397,8 +423,9 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_resident, ms_e2e = float(t[0]), float(t[1])
-    value = P * K / (ms_resident * 1e-3)
-    e2e = P * K / (ms_e2e * 1e-3)
+    pairs_done = P if batch_steps else P * K  # batch steps: the K steps are one pass
+    value = pairs_done / (ms_resident * 1e-3)
+    e2e = pairs_done / (ms_e2e * 1e-3)
 
     # ---- K1 on full-size waves (HBM roofline probe): every local pair scored against one hypothesis ---------------
     # In the pipeline K1 only sees the hypotheses of a round (launch-latency bound); its bandwidth behaviour is measured
@@ -495,7 +522,12 @@ def main():
                        "search": "host pool" if not args.device_search else "device (K6) + host pool, rounds below %d searches on the host pool alone" % args.search_min_batch,
                        "l2": "inputs (%.1f GB of FP64 correspondences) larger than the 126 MB L2" % (P * n_corr * 32 / 1e9),
                        "parallelism": "pairs sharded over %d rank(s), verdict exchange per wave round" % world},
-            "timing": "e2e: K x (prepare + run) back to back; value: the K run() regions (inputs resident), each bracketed by "
+            "step": ("%d queue positions (1/%d of the similarity-ordered queue, cut at the next wave boundary): the %d timed steps "
+                     "are ONE complete pass over the scene, from the empty pose graph to the last committed edge; warm-up = an "
+                     "untimed complete pass before" % (batch, K, K)) if batch_steps else "one complete pass over the scene",
+            "timing": ("e2e: prepare (H2D + K0, in step 0) + the K batches back to back; value: the K batch regions (inputs "
+                       "resident), each bracketed by barrier + synchronize; CUDA events, max over ranks") if batch_steps else
+                      "e2e: K x (prepare + run) back to back; value: the K run() regions (inputs resident), each bracketed by "
                       "barrier + synchronize; CUDA events, max over ranks",
             "step_wall_ms": step_wall,
             "e2e": {"value": e2e, "unit": "pairs/s", "ms_per_step": ms_e2e / K,
@@ -509,8 +541,11 @@ def main():
             "gpu_stage_ms_note": "CUDA-event brackets per context; with the prefetch overlapping the waves the brackets of "
                                  "concurrent contexts include each other's kernels (sums exceed the step's GPU time)",
             "gpu_stage_ms_isolated_fallback_wave": {"pairs": int(len(fb_ids)), **iso},
-            "host_s_per_step": {k: timing.get(k) for k in ("prefetch_s", "waves_s", "total_s", "engine_s", "exchange_s", "host_s",
+            "host_s_per_pass": {k: timing.get(k) for k in ("prefetch_s", "waves_s", "total_s", "engine_s", "exchange_s", "host_s",
                                                             "wait_prefetch_s", "engine_rounds", "exchanges")},
+            "host_s_per_step": {k: (timing.get(k) / K if batch_steps and timing.get(k) is not None else timing.get(k))
+                                for k in ("prefetch_s", "waves_s", "total_s", "engine_s", "exchange_s", "host_s",
+                                          "wait_prefetch_s", "engine_rounds", "exchanges")},
             "search_stats_last_step": search_stats,
             "host_counters": counters, "edges": int(n_edges), "wall_s": wall,
             "branch_mix": {k: int(counters[k]) for k in ("path_accepted", "fallback_accepted", "rejected", "skipped")},

@@ -539,12 +539,26 @@ class PoseGraphBuilder:
 
     def run(self, reconstruction_=None, poseGraph_=None):
         """PoseGraphBuilder::run (pose_graph_builder.h:173-239) -> PoseGraph."""
+        gen = self.run_in_batches(None)
+        while True:
+            try:
+                next(gen)
+            except StopIteration as done:
+                return done.value
+
+    def run_in_batches(self, batch=None):
+        """The same run as a generator: with `batch` set it yields (the number of queue positions committed so far) at the
+        first wave boundary after every further `batch` committed positions, so that a caller can bracket slices of ONE
+        pass — bench.py's steps; the prefetch pipeline keeps running across the yields.  The PoseGraph is the generator's
+        return value (StopIteration.value).  batch=None never yields: that is run()."""
         t0 = time.perf_counter()
         if self.engine is None or not getattr(self, "prepared", False):
             self.prepare()
         t_reg = time.perf_counter()
         host = HostBuilder(self.scene, lazy_fallback=not self.prefetch_fallback, **self.cfg)
         self.host = host
+        total0 = host.remaining()
+        next_mark = int(batch) if batch else None
         if self.gpu_search:
             host.set_search_backend(self.engine, self.gpu_search_min_batch)
         lock = threading.Lock()
@@ -641,6 +655,12 @@ class PoseGraphBuilder:
                     raise _engine.PgiError(f"status {rc}: {lib.pgi_last_error(self.engine.h).decode()}")
                 if rc != WAVE_DONE:
                     raise RuntimeError(f"pgb_run_wave returned {rc}")
+                if next_mark is not None:
+                    left = host.remaining()
+                    if left > 0 and total0 - left >= next_mark:
+                        while total0 - left >= next_mark:
+                            next_mark += int(batch)
+                        yield total0 - left
             prof["engine_s"], prof["host_s"], prof["engine_rounds"] = st.engine_s, st.host_s, int(st.rounds)
         while self.world > 1 or not self.native_loop:
             with progress:
@@ -693,6 +713,13 @@ class PoseGraphBuilder:
                     status = host.wave_status()
                     if status != WAVE_DONE:
                         items = host.next_wave(self.wave_size)
+            if next_mark is not None:
+                with progress:
+                    left = host.remaining()
+                if left > 0 and total0 - left >= next_mark:
+                    while total0 - left >= next_mark:
+                        next_mark += int(batch)
+                    yield total0 - left
         if worker is not None:
             worker.join()
         t_end = time.perf_counter()
