@@ -13,7 +13,8 @@
 // with truncated-quadratic (MSAC) scoring and least-squares local optimisation in place of MAGSAC's
 // sigma-consensus (BASELINE.json north_star: "hypothesis scoring, and least-squares LO refits").
 // PARITY UNPINNED w.r.t. cv2 for this stage: agreement with cv2.findEssentialMat(USAC_MAGSAC) is
-// statistical only and is reported by tests/test_fallback_vs_cv2.py, never assumed.  The CUDA fallback
+// statistical only and is reported by tests/test_oracle_golden.py (the Tier-B test) and scripts/cv2_host_report.py
+// (profiles/r02_cv2_host_report_cfg1_50v.json), never assumed.  The CUDA fallback
 // kernels must match THIS restatement bit-for-bit.  To make that independent of any summation order, every
 // reduction over correspondences is done in exact 64-bit FIXED POINT: each FP64 term is computed with IEEE
 // operations, converted to an integer once, and the integers are summed (associative, so the CUDA kernels are
