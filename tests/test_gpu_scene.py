@@ -48,3 +48,26 @@ def test_accurate_low_noise_scene_takes_path_branch(oracle):
     sc = S.make_scene(n_views=10, n_corr=300, outlier_ratio=0.2, seed=23, n_points=900, noise_px=0.01)
     pgb, ostats = run_and_compare(oracle, sc, prefetch_fallback=False, wave_size=8)
     assert ostats["path_accepted"] + ostats["fallback_accepted"] == ostats["edges"]
+
+
+@pytest.mark.parametrize("native", [True, False])
+def test_a_pass_driven_in_batches_commits_the_same_graph(native):
+    """bench.py's steps are batches of one pass (PoseGraphBuilder.run_in_batches): through the native wave driver and
+    through the Python loop, the batched pass must commit byte for byte what run() commits, and yield once per batch."""
+    sc = S.make_scene(n_views=16, n_corr=300, outlier_ratio=0.3, seed=24, n_points=900)
+    P = len(sc["pair_views"])
+    ref = B.PoseGraphBuilder(kCoreNumber_=4, kSimilarityThreshold_=0.0, scene=sc, wave_size=16, fallback_wave=32, native_loop=native)
+    g_ref = ref.run()
+    pgb = B.PoseGraphBuilder(kCoreNumber_=4, kSimilarityThreshold_=0.0, scene=sc, wave_size=16, fallback_wave=32, native_loop=native)
+    steps = 5
+    gen = pgb.run_in_batches(-(-P // steps))
+    marks, graph = [], None
+    while graph is None:
+        try:
+            marks.append(next(gen))
+        except StopIteration as done:
+            graph = done.value
+    assert graph.edges.tobytes() == g_ref.edges.tobytes() and pgb.log.tobytes() == ref.log.tobytes()
+    assert len(marks) == steps - 1 and all(b > a for a, b in zip(marks, marks[1:]))
+    ref.close()
+    pgb.close()
