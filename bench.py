@@ -513,6 +513,8 @@ def main():
         cores = os.cpu_count() or 1
         tup = tuples_from_log(log, args.cpu_sample or 256 * cores)  # ~10 s of all-core CPU work
         cpu = cpu_pipeline(scene, tup, np.arange(len(tup["pair_id"])))
+        n1 = min(len(tup["pair_id"]), 96)  # the same pipeline on ONE thread (core_number = 1), ~3 s
+        cpu1 = cpu_pipeline(scene, tup, np.unique(np.linspace(0, len(tup["pair_id"]) - 1, n1).astype(np.int64)), threads=1)
         yard = cv2_yardstick(scene, 8 * cores, cores)  # ~1-2 s
         line = {
             "metric": "image_pairs_verified_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
@@ -553,6 +555,7 @@ def main():
                              "sample": "%d evenly spaced (pair, hypothesis) tuples of this run's log, %.1f s; %s; branch mix of the "
                                        "sample: %d path / %d fallback / %d rejected"
                                        % (cpu["pairs"], cpu["seconds"], CPU_NOTE, cpu["path"], cpu["fallback"], cpu["rejected"]),
+                             "single_thread": {"value": cpu1["pairs_per_s"], "unit": "pairs/s", "pairs": cpu1["pairs"]},
                              "third_party_yardstick": yard},
             "fallback_iterations": fb_iters,
             "clocks": clocks,
