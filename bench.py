@@ -103,8 +103,10 @@ def scene_outlier_ratio(name):
 
 def config_keys(name, scene):
     """The workload description both arms print (identical keys and values)."""
-    return {"workload": name, "views": int(len(scene["focal"])), "pairs": int(len(scene["pair_views"])),
-            "corr_per_pair": int(scene["m_offset"][1] - scene["m_offset"][0]), "outlier_ratio": scene_outlier_ratio(name)}
+    P, n_corr = int(len(scene["pair_views"])), int(scene["m_offset"][1] - scene["m_offset"][0])
+    return {"workload": name, "views": int(len(scene["focal"])), "pairs": P, "corr_per_pair": n_corr,
+            "outlier_ratio": scene_outlier_ratio(name),
+            "l2": "inputs (%.1f GB of FP64 correspondences) larger than the 126 MB L2" % (P * n_corr * 32 / 1e9)}
 
 
 # ---- (pair, hypothesis) tuples: what the CPU legs replay ------------------------------------------------------
@@ -520,10 +522,10 @@ def main():
             "metric": "image_pairs_verified_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_resident / K, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {**config_keys(args.config, scene), "wave": args.wave, "fallback": "lazy" if args.lazy else "prefetched",
-                       "search": "host pool" if not args.device_search else "device (K6) + host pool, rounds below %d searches on the host pool alone" % args.search_min_batch,
-                       "l2": "inputs (%.1f GB of FP64 correspondences) larger than the 126 MB L2" % (P * n_corr * 32 / 1e9),
-                       "parallelism": "pairs sharded over %d rank(s), verdict exchange per wave round" % world},
+            "config": config_keys(args.config, scene),  # the workload: identical in both arms
+            "run_config": {"wave": args.wave, "fallback": "lazy" if args.lazy else "prefetched",
+                           "search": "host pool" if not args.device_search else "device (K6) + host pool, rounds below %d searches on the host pool alone" % args.search_min_batch,
+                           "parallelism": "pairs sharded over %d rank(s), verdict exchange per wave round" % world},
             "step": ("%d queue positions (1/%d of the similarity-ordered queue, cut at the next wave boundary): the %d timed steps "
                      "are ONE complete pass over the scene, from the empty pose graph to the last committed edge; warm-up = an "
                      "untimed complete pass before" % (batch, K, K)) if batch_steps else "one complete pass over the scene",
