@@ -278,6 +278,9 @@ pgi_status ensureWave(pgi_ctx *ctx, const Registration &r, uint32_t n, uint32_t 
         ctx->waveCap = cap;
     }
     if ((flags & PGI_WAVE_FALLBACK) && !ctx->fbScratch) {
+        // (after a failed attempt some of these may be allocated: release them first, cudaFree(nullptr) is a no-op)
+        cudaFree(ctx->d_fbSols); cudaFree(ctx->d_fbCounts); cudaFree(ctx->d_fbSolsF); cudaFree(ctx->d_dkList);
+        ctx->d_fbSols = nullptr; ctx->d_fbCounts = nullptr; ctx->d_fbSolsF = nullptr; ctx->d_dkList = nullptr;
         CK(cudaMalloc((void **)&ctx->d_fbSols, (size_t)ctx->waveCap * kFbChunk * 90 * 8));
         CK(cudaMalloc((void **)&ctx->d_fbCounts, (size_t)ctx->waveCap * kFbChunk));
         CK(cudaMalloc((void **)&ctx->d_fbSolsF, (size_t)ctx->waveCap * kFbChunk * 30 * sizeof(float4)));
@@ -288,6 +291,7 @@ pgi_status ensureWave(pgi_ctx *ctx, const Registration &r, uint32_t n, uint32_t 
     if (nHyp > ctx->hypCap) {
         cudaFree(ctx->d_hyp);
         ctx->d_hyp = nullptr;
+        ctx->hypCap = 0;  // (a failed allocation below must not leave a stale capacity behind a null pointer)
         const uint32_t cap = std::max<uint32_t>(nHyp, std::max<uint32_t>(ctx->waveCap, 64));
         CK(cudaMalloc((void **)&ctx->d_hyp, (size_t)cap * 7 * 8));
         ctx->hypCap = cap;
@@ -295,6 +299,7 @@ pgi_status ensureWave(pgi_ctx *ctx, const Registration &r, uint32_t n, uint32_t 
     if ((flags & PGI_WAVE_MASKS) && maskRows > ctx->maskCap) {
         cudaFree(ctx->d_masks);
         ctx->d_masks = nullptr;
+        ctx->maskCap = 0;
         CK(cudaMalloc((void **)&ctx->d_masks, (size_t)maskRows));
         ctx->maskCap = maskRows;
     }
