@@ -10,6 +10,10 @@
 // corrected by the candidate count (:386-399); "too good to be true" ratios are dropped (:402); the caller attaches
 // descriptorDistances[0] to EVERY match when there are at most kMaximumPointNumberForEpipolarHashing of them (:777-779).
 // Eigen pieces (3x3 inverse by cofactors, 3-term products, JacobiSVD) follow pgo_eigen.hpp's conventions.
+// PARITY UNPINNED: the reference has no tests or fixtures for the matcher and cannot be compiled here; what
+// pins this file is its closeness to matcher.h and behavioural tests (tests/test_oracle_matcher.py: matches are true
+// correspondences within 0.75 px of their epipolar lines, selection rule).  atan2 is the host libm's here (the device
+// evaluates the correctly rounded value, which glibc returns for all but ~2.5e-4 of arguments: tests/test_atan2_cr.py).
 #pragma once
 #include <algorithm>
 #include <cmath>
