@@ -27,6 +27,8 @@ def _unit_pose(h):
 
 FB_SCORE = [0.55, 0.10]  # fallback inlier ratio: base, spread (module-level knob of the benchmark script)
 PATH_SCORE = []          # path-branch inlier ratio [base, spread]; empty: ~1.0 (the benchmark script sets the measured mix)
+FB_REJECT = [0]          # [k]: the fallback REJECTS every pair whose hash is 0 mod k (0: never) — sparse-scene behaviour: an edge
+                         # then exists only if a path hypothesis is accepted, i.e. predictions change by edges APPEARING
 
 
 def fake_verdicts(items, n_corr, path_ratio=3, fallback=True):
@@ -51,6 +53,9 @@ def fake_verdicts(items, n_corr, path_ratio=3, fallback=True):
     v["test_count"] = np.where(path_ok, 5, (hh % np.uint64(5)).astype(np.uint32))
     v["accepted"] = 1
     v["branch"] = np.where(path_ok, 1, 2)
+    fb_rejected = np.zeros(n, dtype=bool)
+    if FB_REJECT[0]:
+        fb_rejected = ~path_ok & (hp % np.uint64(FB_REJECT[0]) == 0)
     inl_path = n_corr - (hh % np.uint64(max(1, n_corr // 100))).astype(np.uint32)
     if PATH_SCORE:
         inl_path = (PATH_SCORE[0] * n_corr + (hh % np.uint64(max(1, int(n_corr * PATH_SCORE[1]))))).astype(np.uint32)
@@ -61,6 +66,9 @@ def fake_verdicts(items, n_corr, path_ratio=3, fallback=True):
     pose = np.where(path_ok[:, None], _unit_pose(hh), _unit_pose(hp))
     v["q"], v["t"] = pose[:, :4], pose[:, 4:]
     v["E"] = 0.0
+    v["accepted"][fb_rejected] = 0
+    v["branch"][fb_rejected] = 0
+    v["inlier_count"][fb_rejected] = 0
     if not fallback:
         failed = ~path_ok
         v["accepted"][failed] = 0

@@ -228,7 +228,8 @@ def test_both_directions_of_a_pair_queued_in_one_wave():
         assert ed.tobytes() == logs[0][1].tobytes()
 
 
-def test_cost_floor_and_fine_staleness_keep_the_sequential_result_on_a_dense_graph(monkeypatch):
+@pytest.mark.parametrize("fb_reject", [0, 4])
+def test_cost_floor_and_fine_staleness_keep_the_sequential_result_on_a_dense_graph(monkeypatch, fb_reject):
     """Dense ring-camera view graph with the benchmark scenes' score mix (path-branch edges score LOWER than the fallback
     edges they replace).  Two exactness claims of pgb_host.cpp are exercised at once: searches run with a cost floor
     (children below it skip the push_heap climb) and a search result survives a changed edge at an expanded vertex when
@@ -238,6 +239,7 @@ def test_cost_floor_and_fine_staleness_keep_the_sequential_result_on_a_dense_gra
 
     monkeypatch.setattr(fake_verdicts, "FB_SCORE", [0.29, 0.06])
     monkeypatch.setattr(fake_verdicts, "PATH_SCORE", [0.06, 0.19])
+    monkeypatch.setattr(fake_verdicts, "FB_REJECT", [fb_reject])  # 4: a quarter of the fallbacks reject (edges appear / stay absent)
     sc = dense_scene(110, n_corr=2000, seed=5, ring_cameras=True)
     logs = []
     for wave, threads in ((1, 1), (64, 4), (256, 8)):
@@ -246,6 +248,7 @@ def test_cost_floor_and_fine_staleness_keep_the_sequential_result_on_a_dense_gra
         logs.append((host.log().copy(), host.edges().copy(), host.counters()))
         host.close()
     c = logs[2][2]
+    assert (c["rejected"] > 300) == bool(fb_reject)
     assert c["path_accepted"] > 1000 and c["astar_reruns"] > 0
     assert c["stale_spared"] > 0  # the fine rule kept results the coarse rule would have searched again
     for lg, ed, _ in logs[1:]:
