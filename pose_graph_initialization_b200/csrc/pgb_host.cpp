@@ -676,6 +676,20 @@ struct Change {  // a wave position whose actual outcome differs from the predic
 // PGB_FINE_STALENESS=0: a changed edge at an expanded vertex always invalidates the search (the coarse rule)
 static const bool kFineStaleness = !(getenv("PGB_FINE_STALENESS") && atoi(getenv("PGB_FINE_STALENESS")) == 0);
 
+// The fine staleness rule for ONE expansion of a search: the expansion's node had the cost tuple (c0, c1), `h` is the
+// heuristic of the changed edge's other endpoint, the edge's score goes sOld -> sNew, tauMin is the smallest combined cost
+// the search popped.  The child pushed through the edge costs weight * min(c0, score) + (1 - weight) * max(c1, h)
+// (graph_traversal.h:843-852, same operations); if that is below tauMin under both scores, the child is an entry that
+// never leaves the queue and whose value decides nothing (aStar's cost-floor argument with floor = tauMin), so the search
+// is bit for bit the same with either score.
+inline bool scoreChangeIsInert(double c0, double c1, double h, double sOld, double sNew, double wgt, double omw, double tauMin)
+{
+    const double nd = c1 < h ? h : c1;
+    const double fOld = wgt * (c0 > sOld ? sOld : c0) + omw * nd;
+    const double fNew = wgt * (c0 > sNew ? sNew : c0) + omw * nd;
+    return fOld < tauMin && fNew < tauMin;
+}
+
 struct HypKey {
     uint32_t pair;
     uint64_t bits[7];
@@ -1345,11 +1359,7 @@ uint32_t advanceWave(pgb_builder *b)
                         if (c.k >= m) break;  // (lists are in position order)
                         if (c.existence) { it.searched = false; break; }
                         const uint32_t other = c.u == v ? c.w : c.u;
-                        const double h = simTo[other];
-                        const double nd = c1 < h ? h : c1;
-                        const double fOld = wgt * (c0 > c.sOld ? c.sOld : c0) + omw * nd;  // graph_traversal.h:843-852
-                        const double fNew = wgt * (c0 > c.sNew ? c.sNew : c0) + omw * nd;
-                        if (!(fOld < it.tauMin) || !(fNew < it.tauMin)) { it.searched = false; break; }
+                        if (!scoreChangeIsInert(c0, c1, simTo[other], c.sOld, c.sNew, wgt, omw, it.tauMin)) { it.searched = false; break; }
                     }
                 }
                 if (it.searched) ++b->ctr.stale_spared;  // (counts positions that were examined and kept)
